@@ -1,0 +1,125 @@
+/* schnorr_b200 -- C ABI of the B200-native Schnorr verification engine (Cheetah curve / Rescue hash).
+ *
+ * This is the drop-in boundary for the hot path of toposware/schnorr-sig.  The reference has no FFI
+ * (`#![deny(unsafe_code)]`, src/lib.rs:152); the entry points below are what a `schnorr-sig-sys`
+ * layer under the reference's public API would bind (INTEGRATION.md shows the Rust side).  Each
+ * function cites the reference interface it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes, no CUDA/torch types; `void *stream` is a cudaStream_t.
+ *  - record layouts are the reference's own byte encodings:
+ *      signature  81 B  = CompressedPoint (48 B little-endian limbs c0..c5 of R.x, 1 flag byte:
+ *                         bit 7 infinity, bit 6 y-sign) || Scalar e (32 B LE)    src/signature.rs:208-214
+ *      public key 96 B  = affine x (48 B) || y (48 B), the in-memory `PublicKey(AffinePoint)`
+ *                         (src/public.rs:24) + one byte per key: 1 = identity
+ *      scalar     32 B  little-endian                                            src/constants.rs:12
+ *      messages   one byte blob + uint64 offsets[n+1]  (the reference's `&[&[u8]]`)
+ *  - verdict bytes: 0 = Ok(()), 1 = Err(InvalidPublicKey), 2 = Err(InvalidSignature)
+ *    (src/error.rs:13-18), 3 = malformed input on which the reference panics or which its types
+ *    cannot represent (non-canonical limb / scalar >= q; src/signature.rs:186, src/batch.rs:67,104).
+ *  - return value: 0 on success, negative SCHNORR_B200_E* on argument / CUDA failure.  An invalid
+ *    signature is data (a verdict), never an error code.
+ *  - `*_dev` variants take DEVICE pointers for every buffer, enqueue on the context stream and do
+ *    not synchronise; the host variants copy in, run the same kernels, copy out and synchronise.
+ *  - a context is single-owner: one in-flight call per context; create several for concurrency.
+ *  - there is NO CPU fallback: without a CUDA device `schnorr_b200_create` fails.
+ */
+#ifndef SCHNORR_B200_H
+#define SCHNORR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCHNORR_B200_OK 0
+#define SCHNORR_B200_EARG (-1)    /* bad argument */
+#define SCHNORR_B200_ECUDA (-2)   /* CUDA runtime failure, see schnorr_b200_last_error */
+#define SCHNORR_B200_ENODEV (-3)  /* no usable CUDA device */
+
+#define SCHNORR_B200_SIGNATURE_BYTES 81   /* SIGNATURE_LENGTH   src/constants.rs:30 */
+#define SCHNORR_B200_POINT_BYTES 96       /* affine x||y */
+#define SCHNORR_B200_COMPRESSED_BYTES 49  /* PUBLIC_KEY_LENGTH  src/constants.rs:24 */
+#define SCHNORR_B200_SCALAR_BYTES 32      /* SCALAR_LENGTH      src/constants.rs:12 */
+#define SCHNORR_B200_DIGEST_BYTES 32
+#define SCHNORR_B200_PARTIAL_BYTES 192    /* Jacobian point 144 B || partial scalar 32 B || flags 16 B */
+
+typedef struct schnorr_b200_ctx schnorr_b200_ctx;
+
+/* Creates a context on CUDA device `device`: stream, scratch arena and the fixed-base table of G
+ * (the reference's `cheetah::BASEPOINT_TABLE`, src/signature.rs:19) built on the device. */
+int schnorr_b200_create(int device, schnorr_b200_ctx **out);
+void schnorr_b200_destroy(schnorr_b200_ctx *ctx);
+const char *schnorr_b200_last_error(const schnorr_b200_ctx *ctx);
+/* Use an external stream (e.g. the caller's current stream) for all subsequent work. NULL = own stream. */
+int schnorr_b200_set_stream(schnorr_b200_ctx *ctx, void *stream);
+int schnorr_b200_synchronize(schnorr_b200_ctx *ctx);
+/* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
+uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx *ctx);
+/* Device time (CUDA events on the context stream) of the dominant kernel of the last *_dev call:
+ * k_verify (verify_many), k_hash (hash_messages), k_msm_bucket_sum (batch).  Synchronises on it. */
+int schnorr_b200_last_kernel_ms(schnorr_b200_ctx *ctx, float *ms);
+
+/* hash_message(&Fp6, &PublicKey, &[u8]) -> [u8; 32]            src/signature.rs:274-306
+ * rx48: n x 48 B (R.x limbs), pk96: n x 96 B, digests: n x 32 B.  */
+int schnorr_b200_hash_messages(schnorr_b200_ctx *ctx, size_t n, const uint8_t *rx48, const uint8_t *pk96,
+                               const uint8_t *msgs, const uint64_t *msg_off, uint8_t *digests);
+int schnorr_b200_hash_messages_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *rx48, const uint8_t *pk96,
+                                   const uint8_t *msgs, const uint64_t *msg_off, uint8_t *digests);
+
+/* Signature::verify(self, message, &PublicKey) for n independent triples  src/signature.rs:181-205
+ * (also PublicKey::verify_signature :170-176, KeyPair::verify_signature :159-165,
+ *  KeyedSignature::verify :232-234).  pk_inf may be NULL (no identity keys). */
+int schnorr_b200_verify_many(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
+                             const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                             uint8_t *verdicts);
+int schnorr_b200_verify_many_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
+                                 const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                                 uint8_t *verdicts);
+
+/* verify_batch(&[Signature], &[PublicKey], &[&[u8]], rng)                  src/batch.rs:31-50
+ * = generate_batch_coefficients (:56-81) + verify_prepared_batch (:84-130).
+ * rand32: n x 32 B caller-supplied randomisers s_i (reduced mod q) -- the seam the reference has at
+ * verify_prepared_batch.  *verdict: 0 / 2 / 3.  lhs97 / rhs97 (optional): affine x||y||inf of
+ * sum s_i R_i - sum s_i h_i P_i  and of (sum s_i e_i) G  for bit-exact comparison. */
+int schnorr_b200_verify_batch(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
+                              const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                              const uint8_t *rand32, int *verdict, uint8_t *lhs97, uint8_t *rhs97);
+/* Multi-GPU form: each rank reduces its slice to one 192-byte partial (device buffer), the caller
+ * gathers the partials (one small NCCL gather) and any rank finishes.  */
+int schnorr_b200_batch_partial_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
+                                   const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                                   const uint8_t *rand32, uint8_t *partial192);
+int schnorr_b200_batch_finish_dev(schnorr_b200_ctx *ctx, size_t n_partials, const uint8_t *partials192,
+                                  uint8_t *result216 /* device, 216 B: verdict(1) pad(7) lhs97 pad(7) rhs97 pad(7) */);
+int schnorr_b200_batch_finish(schnorr_b200_ctx *ctx, size_t n_partials, const uint8_t *partials192_host,
+                              int *verdict, uint8_t *lhs97, uint8_t *rhs97);
+
+/* PublicKey::from(&PrivateKey) = BASEPOINT_TABLE * sk                      src/public.rs:26-32 */
+int schnorr_b200_keygen(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sk32, uint8_t *pk96, uint8_t *pk_inf);
+int schnorr_b200_keygen_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sk32, uint8_t *pk96, uint8_t *pk_inf);
+/* KeyPair::sign(&self, message, rng) with the nonce r supplied by the caller  src/signature.rs:114-129 */
+int schnorr_b200_sign_many(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sk32, const uint8_t *pk96,
+                           const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                           const uint8_t *nonce32, uint8_t *sigs81);
+int schnorr_b200_sign_many_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sk32, const uint8_t *pk96,
+                               const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                               const uint8_t *nonce32, uint8_t *sigs81);
+
+/* PublicKey::from_bytes / AffinePoint::from_compressed for n 49-byte records  src/public.rs:54-56
+ * ok[i] = 1 when the record decodes (CtOption is_some). */
+int schnorr_b200_decompress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *in49, uint8_t *pk96, uint8_t *pk_inf,
+                            uint8_t *ok);
+/* AffinePoint::to_compressed / PublicKey::to_bytes                           src/public.rs:49-51 */
+int schnorr_b200_compress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *pk96, const uint8_t *pk_inf,
+                          uint8_t *out49);
+
+/* Integer-multiply roofline calibration: runs a register-resident chain of `iters` dependent-free
+ * 32x32->64 multiply-adds per thread on a full grid and returns wide multiplies per second. */
+int schnorr_b200_imad_peak(schnorr_b200_ctx *ctx, int iters, double *wide_mul_per_s, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCHNORR_B200_H */

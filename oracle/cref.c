@@ -397,7 +397,16 @@ static aff load_pk(const u8 *pk96, const u8 *pk_inf, u64 i) {
     return p;
 }
 /* Signature::verify, src/signature.rs:181-205 -> 0 ok, 1 InvalidPublicKey, 2 InvalidSignature, 3 malformed (reference panics) */
+static int pk_canonical(const u8 *pk96, u64 i) {
+    for (int k = 0; k < 12; k++) { u64 v; memcpy(&v, pk96 + 96 * i + 8 * k, 8); if (v >= PP) return 0; }
+    return 1;
+}
+static int scalar_canonical(const u8 *b32) { u64 t[4]; memcpy(t, b32, 32); return !sc_geq_q(t); }
+/* States the reference's types cannot hold (Scalar >= q, Fp limb >= p inside a PublicKey) are
+ * reported as 3 before anything else; a canonical-but-off-subgroup key is 1; a non-canonical sig.x
+ * limb (Fp6::from_bytes(..).unwrap() panics AFTER the subgroup check, :182-186) is 3. */
 static u8 verify_one(const u8 *sig81, aff pk, const u8 *msg, u64 len) {
+    if (!scalar_canonical(sig81 + 49)) return 3;
     if (!is_torsion_free(pk)) return 1;
     fp6 x;
     if (!f6_from_bytes(sig81, &x)) return 3; /* flag byte sig81[48] ignored */
@@ -429,7 +438,9 @@ static void run_jobs(void *(*fn)(void *), job *tmpl, int nt) {
 static void *verify_worker(void *arg) {
     job *j = arg;
     for (u64 i = j->tid; i < j->n; i += j->nt)
-        j->o1[i] = verify_one(j->a + 81 * i, load_pk(j->b, j->c, i), j->d + j->off[i], j->off[i + 1] - j->off[i]);
+        j->o1[i] = (!(j->c && j->c[i]) && !pk_canonical(j->b, i))
+                       ? 3
+                       : verify_one(j->a + 81 * i, load_pk(j->b, j->c, i), j->d + j->off[i], j->off[i + 1] - j->off[i]);
     return 0;
 }
 API int cref_verify_many(u64 n, const u8 *sigs81, const u8 *pk96, const u8 *pk_inf, const u8 *msgs,
@@ -502,6 +513,7 @@ static void *batch_worker(void *arg) {
         const u8 *sig = j->a + 81 * i;
         aff pk = load_pk(j->b, j->c, i);
         fp6 x;
+        if (!scalar_canonical(sig + 49) || (!(j->c && j->c[i]) && !pk_canonical(j->b, i))) { j->bad = 1; break; }
         if (!f6_from_bytes(sig, &x)) { j->bad = 1; break; }            /* unwrap panic, batch.rs:67 */
         u8 h[32];
         hash_message(x, pk, j->d + j->off[i], j->off[i + 1] - j->off[i], h);

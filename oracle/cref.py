@@ -171,3 +171,18 @@ def scalar_reduce(a32):
     r = np.zeros(32, dtype=np.uint8)
     lib().cref_scalar_reduce(_p(_u8(a32)), _p(r))
     return r
+
+
+def workload(seed, n, msg_len, nthreads=1):
+    """Seeded keys / messages / valid signatures produced entirely by this oracle (used by the CPU
+    baseline legs of bench.py and by tests)."""
+    rng = np.random.default_rng(seed)
+    sk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sk[:, 31] &= 0x3F
+    nonce = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    nonce[:, 31] &= 0x3F
+    blob = rng.integers(0, 256, n * msg_len, dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(msg_len)
+    pk, inf = keygen(sk, nthreads)
+    sigs = sign_many(sk, pk, inf, blob, off, nonce, nthreads)
+    return dict(sk=sk, nonce=nonce, blob=blob, off=off, pk=pk, inf=inf, sigs=sigs)

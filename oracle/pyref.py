@@ -481,13 +481,15 @@ OK, INVALID_PUBLIC_KEY, INVALID_SIGNATURE, MALFORMED = 0, 1, 2, 3
 def verify(sig_x49: bytes, e: int, message: bytes, pk) -> int:
     """Signature::verify src/signature.rs:181-205 -> verdict code (0 ok, 1 InvalidPublicKey,
     2 InvalidSignature, 3 = the reference panics: non-canonical x limb, :186)."""
+    if e >= Q or (pk is not INF and any(c >= P for c in pk[0] + pk[1])):
+        return MALFORMED                     # states the reference's Scalar / Fp types cannot hold
     if not is_torsion_free(pk):
         return INVALID_PUBLIC_KEY
     x = f6_from_bytes(sig_x49[:48])          # flag byte ignored
     if x is None:
         return MALFORMED
     h = scalar_from_digest(hash_message(x, pk, message))
-    r = pt_mul2(pk, h, generator(), e % Q)
+    r = pt_mul2(pk, h, generator(), e)
     rx = F6_ZERO if r is INF else r[0]       # identity reads as x = 0
     return OK if rx == x else INVALID_SIGNATURE
 

@@ -1,0 +1,58 @@
+"""ctypes binding of the C ABI (include/schnorr_b200.h).  Fails loudly when the CUDA library is
+missing or cannot be built: there is no CPU fallback."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+_u8p = C.c_void_p
+_sz = C.c_size_t
+
+_SIGNATURES = {
+    "schnorr_b200_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "schnorr_b200_destroy": (None, [C.c_void_p]),
+    "schnorr_b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "schnorr_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "schnorr_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "schnorr_b200_launch_count": (C.c_uint64, [C.c_void_p]),
+    "schnorr_b200_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "schnorr_b200_hash_messages": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 5),
+    "schnorr_b200_hash_messages_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 5),
+    "schnorr_b200_verify_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6),
+    "schnorr_b200_verify_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6),
+    "schnorr_b200_verify_batch": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6 + [C.POINTER(C.c_int), _u8p, _u8p]),
+    "schnorr_b200_batch_partial_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
+    "schnorr_b200_batch_finish_dev": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p]),
+    "schnorr_b200_batch_finish": (C.c_int, [C.c_void_p, _sz, _u8p, C.POINTER(C.c_int), _u8p, _u8p]),
+    "schnorr_b200_keygen": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
+    "schnorr_b200_keygen_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
+    "schnorr_b200_sign_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
+    "schnorr_b200_sign_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
+    "schnorr_b200_decompress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
+    "schnorr_b200_compress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
+    "schnorr_b200_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def library_path():
+    return _build.SO
+
+
+def lib():
+    """Loads (building first if stale) schnorr-sig_b200/csrc/libschnorr_b200.so."""
+    global _LIB
+    if _LIB is None:
+        so = _build.build()
+        if not os.path.exists(so):
+            raise RuntimeError("libschnorr_b200.so is missing and could not be built; there is no CPU fallback")
+        L = C.CDLL(so)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError here = ABI drift against include/schnorr_b200.h
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB

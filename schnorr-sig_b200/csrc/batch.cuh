@@ -1,0 +1,473 @@
+// Random-linear-combination batch verification (reference src/batch.rs:31-130) as a Pippenger
+// bucket multi-scalar multiplication.  Included by schnorr_b200.cu (single translation unit).
+//
+//   check   sum s_i R_i - sum (s_i h_i) P_i == (sum s_i e_i) G      (x-only, src/batch.rs:121-129)
+//
+//   k_batch_prepare   K3: per signature: challenge hash, h_i mod q, s_i e_i, s_i h_i, decompress R_i,
+//                     negate P_i -> 2n affine points + 2n scalars
+//   k_msm_count / k_msm_scatter   signed c-bit digits -> counting sort of point indices by bucket
+//   k_msm_bucket_sum  one bucket per thread, mixed additions of its (sorted) points
+//   k_msm_window_sum  running-sum reduction of bucket chunks + chunk offsets
+//   k_msm_window_fold per-window total
+//   k_msm_horner      sum_k 2^(ck) W_k  -> one Jacobian partial per GPU
+//   k_batch_finish    adds the per-GPU partials, (sum lin) * G, x-only comparison
+// The bucket sums are order-independent group elements, so the atomics-based (non-deterministic)
+// slot assignment inside a bucket does not affect the bit-exact result.
+#pragma once
+
+struct msm_plan {
+    int c;        // window bits
+    int K;        // windows
+    int B;        // buckets per window = 2^(c-1), ids 1..B
+    int chunks;   // threads per window in the window-sum stage
+    int chunk_sz; // buckets per chunk
+};
+
+static msm_plan msm_make_plan(size_t npoints) {
+    double best = 1e300;
+    msm_plan p{};
+    for (int c = 4; c <= 16; c++) {
+        int K = (256 + c - 1) / c;
+        double B = (double)(1u << (c - 1));
+        double cost = (double)npoints * K + 3.0 * K * B;
+        if (cost < best) {
+            best = cost;
+            p.c = c;
+            p.K = K;
+            p.B = 1 << (c - 1);
+        }
+    }
+    p.chunk_sz = p.B >= 32 ? 32 : p.B;
+    p.chunks = p.B / p.chunk_sz;
+    return p;
+}
+
+// ---- K3 ----------------------------------------------------------------------------------------
+// pts: 2n affine points as 12 x u64 (x||y); scalars: 2n x 8 x u32; lin: n scalars s_i e_i
+__global__ void __launch_bounds__(128) k_batch_prepare(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                       const uint64_t* __restrict__ msg_off,
+                                                       const uint8_t* __restrict__ rand32, uint64_t* __restrict__ pts,
+                                                       uint32_t* __restrict__ scalars, uint32_t* __restrict__ lin,
+                                                       int* __restrict__ bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = in.n;
+    if (i >= n) return;
+    uint8_t fl = in.flags[i];
+    fp6 sx = load_fp6_planes(in.planes, 0, n, i);
+    scalar e = load_scalar_planes(in.planes, 3, n, i);
+    fp6 px = load_fp6_planes(in.planes, 5, n, i);
+    fp6 py = load_fp6_planes(in.planes, 8, n, i);
+    bool pk_inf = fl & FL_PK_INF;
+    bool ok = !(fl & (FL_MALFORMED | FL_X_BAD));
+    scalar s = sc_from_u256(sc_load_le(rand32 + 32 * i));
+    scalar s_r = sc_zero(), s_p = sc_zero(), l = sc_zero();
+    fp6 rx = fp6_zero(), ry = fp6_zero();
+    if (ok) {
+        bool r_inf;
+        ok = decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);  // unwrap panic, src/batch.rs:104
+        if (ok) {
+            uint64_t off = msg_off[i];
+            scalar h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+            l = sc_mul(s, e);                     // src/batch.rs:92-97
+            s_r = r_inf ? sc_zero() : s;          // identity contributes nothing
+            s_p = pk_inf ? sc_zero() : sc_mul(h, s);  // src/batch.rs:109-111
+        }
+    }
+    if (!ok) atomicOr(bad, 1);
+    fp6 npy = fp6_neg(py);  // src/batch.rs:106
+    uint64_t* o = pts + i * 12;
+    uint64_t* o2 = pts + (n + i) * 12;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        o[k] = rx.c[k];
+        o[6 + k] = ry.c[k];
+        o2[k] = px.c[k];
+        o2[6 + k] = npy.c[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        scalars[i * 8 + k] = s_r.l[k];
+        scalars[(n + i) * 8 + k] = s_p.l[k];
+        lin[i * 8 + k] = l.l[k];
+    }
+}
+
+// sum of m scalars mod q: each block writes one partial into out[blockIdx.x]
+__global__ void __launch_bounds__(256) k_scalar_sum(const uint32_t* __restrict__ in, size_t m, uint32_t* __restrict__ out) {
+    __shared__ uint32_t sh[256 * 8];
+    scalar acc = sc_zero();
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (size_t)gridDim.x * blockDim.x) {
+        scalar v;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v.l[k] = in[j * 8 + k];
+        acc = sc_add(acc, v);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sh[threadIdx.x * 8 + k] = acc.l[k];
+    __syncthreads();
+    for (int stride = 128; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            scalar a, b;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                a.l[k] = sh[threadIdx.x * 8 + k];
+                b.l[k] = sh[(threadIdx.x + stride) * 8 + k];
+            }
+            a = sc_add(a, b);
+#pragma unroll
+            for (int k = 0; k < 8; k++) sh[threadIdx.x * 8 + k] = a.l[k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 8) out[blockIdx.x * 8 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// ---- K4: Pippenger ---------------------------------------------------------------------------
+// signed digit of window k given the running carry; returns bucket id (0 = none) and sign
+__device__ __forceinline__ int msm_digit(const scalar& s, int k, int c, int& carry, bool& neg) {
+    int raw = (int)sc_bits(s, k * c, c) + carry;
+    int half = 1 << (c - 1);
+    neg = raw > half;
+    carry = neg ? 1 : 0;
+    return neg ? (1 << c) - raw : raw;
+}
+
+__global__ void __launch_bounds__(256) k_msm_count(const uint32_t* __restrict__ scalars, size_t npts, msm_plan pl,
+                                                   uint32_t* __restrict__ counts) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    scalar s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.l[k] = scalars[j * 8 + k];
+    int carry = 0;
+    for (int k = 0; k < pl.K; k++) {
+        bool neg;
+        int b = msm_digit(s, k, pl.c, carry, neg);
+        if (b) atomicAdd(&counts[(size_t)k * (pl.B + 1) + b], 1u);
+    }
+}
+
+// single-block exclusive scan of m counters (m up to a few million): offsets[i] = sum counts[< i]
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ counts, size_t m,
+                                                         uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    size_t per = (m + 1023) / 1024;
+    size_t lo = (size_t)threadIdx.x * per, hi = lo + per < m ? lo + per : m;
+    uint32_t sum = 0;
+    for (size_t i = lo; i < hi; i++) sum += counts[i];
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partials
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t v = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = sh[threadIdx.x] - sum;
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t c = counts[i];
+        offsets[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ scalars, size_t npts, msm_plan pl,
+                                                     const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                                                     uint32_t* __restrict__ sorted) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npts) return;
+    scalar s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.l[k] = scalars[j * 8 + k];
+    int carry = 0;
+    for (int k = 0; k < pl.K; k++) {
+        bool neg;
+        int b = msm_digit(s, k, pl.c, carry, neg);
+        if (b) {
+            size_t slot = (size_t)k * (pl.B + 1) + b;
+            uint32_t pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
+            sorted[pos] = (uint32_t)j | (neg ? 0x80000000u : 0u);
+        }
+    }
+}
+
+__device__ __forceinline__ void load_affine(const uint64_t* __restrict__ pts, size_t j, fp6& x, fp6& y) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pts + j * 12);
+    ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3], e = p[4], f = p[5];
+    x = fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
+    y = fp6{{d.x, d.y, e.x, e.y, f.x, f.y}};
+}
+
+// one bucket per thread
+__global__ void __launch_bounds__(128) k_msm_bucket_sum(const uint64_t* __restrict__ pts, msm_plan pl,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ sorted, jac_pt* __restrict__ buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)pl.K * pl.B;
+    if (t >= total) return;
+    int k = (int)(t / pl.B), b = (int)(t % pl.B) + 1;
+    size_t slot = (size_t)k * (pl.B + 1) + b;
+    uint32_t beg = offsets[slot], cnt = counts[slot];
+    jac_pt acc = jac_identity();
+    for (uint32_t u = 0; u < cnt; u++) {
+        uint32_t v = sorted[beg + u];
+        fp6 x, y;
+        load_affine(pts, v & 0x7fffffffu, x, y);
+        if (v >> 31) y = fp6_neg(y);
+        acc = jac_madd(acc, x, y, false);
+    }
+    buckets[t] = acc;
+}
+
+// small multiple m * P by double-and-add (m < 2^20)
+__device__ jac_pt jac_mul_small(const jac_pt& P, uint32_t m) {
+    jac_pt acc = jac_identity();
+    for (int bit = 19; bit >= 0; bit--) {
+        acc = jac_dbl(acc);
+        if ((m >> bit) & 1) acc = jac_add(acc, P);
+    }
+    return acc;
+}
+
+// chunk t of window k covers buckets lo..lo+chunk_sz-1 (1-based ids): contributes
+//   sum_b b * B_b = sum_b (b - lo + 1) B_b + (lo - 1) * sum_b B_b
+__global__ void __launch_bounds__(64) k_msm_window_sum(msm_plan pl, const jac_pt* __restrict__ buckets,
+                                                       jac_pt* __restrict__ chunk_out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pl.K * pl.chunks) return;
+    int k = t / pl.chunks, ch = t % pl.chunks;
+    int lo = ch * pl.chunk_sz + 1;
+    const jac_pt* bk = buckets + (size_t)k * pl.B + (lo - 1);
+    jac_pt running = jac_identity(), acc = jac_identity();
+    for (int b = pl.chunk_sz - 1; b >= 0; b--) {
+        running = jac_add(running, bk[b]);
+        acc = jac_add(acc, running);
+    }
+    if (lo > 1) acc = jac_add(acc, jac_mul_small(running, (uint32_t)(lo - 1)));
+    chunk_out[t] = acc;
+}
+__global__ void k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out, jac_pt* __restrict__ windows) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pl.K) return;
+    jac_pt acc = jac_identity();
+    for (int ch = 0; ch < pl.chunks; ch++) acc = jac_add(acc, chunk_out[(size_t)k * pl.chunks + ch]);
+    windows[k] = acc;
+}
+// partial192 = Jacobian point (18 u64) || partial scalar sum (4 u64) || bad flag (u64) || pad
+__global__ void k_msm_horner(msm_plan pl, const jac_pt* __restrict__ windows, const uint32_t* __restrict__ lin,
+                             const int* __restrict__ bad, uint64_t* __restrict__ partial) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    jac_pt acc = windows[pl.K - 1];
+    for (int k = pl.K - 2; k >= 0; k--) {
+        for (int s = 0; s < pl.c; s++) acc = jac_dbl(acc);
+        acc = jac_add(acc, windows[k]);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        partial[c] = acc.X.c[c];
+        partial[6 + c] = acc.Y.c[c];
+        partial[12 + c] = acc.Z.c[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) partial[18 + c] = ((uint64_t)lin[2 * c + 1] << 32) | lin[2 * c];
+    partial[22] = (uint64_t)(*bad != 0);
+    partial[23] = 0;
+}
+
+// result200: [0] verdict, [8..105) lhs97, [104..201)... laid out as verdict(1) pad(7) lhs(97) pad(7) rhs(97)
+static constexpr size_t RESULT_BYTES = 216;
+__global__ void k_batch_finish(size_t np, const uint64_t* __restrict__ partials, const uint64_t* __restrict__ gtab,
+                               uint8_t* __restrict__ result) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    jac_pt acc = jac_identity();
+    scalar lin = sc_zero();
+    bool bad = false;
+    for (size_t r = 0; r < np; r++) {
+        const uint64_t* p = partials + r * 24;
+        jac_pt t;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            t.X.c[c] = p[c];
+            t.Y.c[c] = p[6 + c];
+            t.Z.c[c] = p[12 + c];
+        }
+        acc = jac_add(acc, t);
+        lin = sc_add(lin, sc_from_u64x4(p[18], p[19], p[20], p[21]));
+        bad |= p[22] != 0;
+    }
+    fp6 lx, ly, rx, ry;
+    bool linf, rinf;
+    jac_to_affine(acc, lx, ly, linf);
+    jac_to_affine(fixed_base_mul(lin, gtab), rx, ry, rinf);  // src/batch.rs:98-100
+    uint8_t v = bad ? VERDICT_MALFORMED : (fp6_eq(lx, rx) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE);
+    result[0] = v;
+    uint64_t* l = reinterpret_cast<uint64_t*>(result + 8);
+    uint64_t* rr = reinterpret_cast<uint64_t*>(result + 112);
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        l[c] = lx.c[c];
+        l[6 + c] = ly.c[c];
+        rr[c] = rx.c[c];
+        rr[6 + c] = ry.c[c];
+    }
+    result[8 + 96] = linf ? 1 : 0;
+    result[112 + 96] = rinf ? 1 : 0;
+}
+
+// ---- host orchestration ----------------------------------------------------------------------
+static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                              const uint8_t* rand32, uint8_t* partial192) {
+    soa_batch soa;
+    if (int rc = alloc_soa(ctx, n, &soa)) return rc;
+    size_t npts = 2 * n;
+    if (npts >= 0x7fffffffu) {
+        ctx->err = "batch too large for 31-bit point indices";
+        return SCHNORR_B200_EARG;
+    }
+    msm_plan pl = msm_make_plan(npts);
+    size_t nslots = (size_t)pl.K * (pl.B + 1);
+    void *d_pts, *d_sc, *d_lin, *d_cnt, *d_sorted, *d_buckets, *d_small;
+    if (int rc = ensure_scratch(ctx, SL_D, npts * 96, &d_pts)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, npts * 32, &d_sc)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_F, n * 32 + 512 * 32, &d_lin)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_G, nslots * 4 * 3, &d_cnt)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_J, npts * pl.K * 4, &d_sorted)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_K, sizeof(jac_pt) * ((size_t)pl.K * pl.B + (size_t)pl.K * pl.chunks + pl.K), &d_buckets))
+        return rc;
+    if (int rc = ensure_scratch(ctx, SL_L, 64, &d_small)) return rc;
+    uint32_t* counts = (uint32_t*)d_cnt;
+    uint32_t* offsets = counts + nslots;
+    uint32_t* cursor = offsets + nslots;
+    jac_pt* buckets = (jac_pt*)d_buckets;
+    jac_pt* chunk_out = buckets + (size_t)pl.K * pl.B;
+    jac_pt* windows = chunk_out + (size_t)pl.K * pl.chunks;
+    uint32_t* lin = (uint32_t*)d_lin;
+    uint32_t* lin_part = lin + n * 8;       // 256 partials
+    uint32_t* lin_total = lin_part + 256 * 8;
+    int* bad = (int*)d_small;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, nslots * 4 * 3, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_small, 0, 64, st));
+    k_ingest<<<grid_for(n, INGEST_THREADS), INGEST_THREADS, 0, st>>>(n, sigs81, pk96, pk_inf, soa);
+    k_batch_prepare<<<grid_for(n, 128), 128, 0, st>>>(soa, msgs, msg_off, rand32, (uint64_t*)d_pts, (uint32_t*)d_sc, lin, bad);
+    int sum_blocks = (int)((n + 255) / 256);
+    if (sum_blocks > 256) sum_blocks = 256;
+    k_scalar_sum<<<sum_blocks, 256, 0, st>>>(lin, n, lin_part);
+    k_scalar_sum<<<1, 256, 0, st>>>(lin_part, (size_t)sum_blocks, lin_total);
+    k_msm_count<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, counts);
+    k_exclusive_scan<<<1, 1024, 0, st>>>(counts, nslots, offsets);
+    k_msm_scatter<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, offsets, cursor, (uint32_t*)d_sorted);
+    cudaEventRecord(ctx->ev_k0, st);
+    k_msm_bucket_sum<<<grid_for((size_t)pl.K * pl.B, 128), 128, 0, st>>>((uint64_t*)d_pts, pl, offsets, counts,
+                                                                         (uint32_t*)d_sorted, buckets);
+    cudaEventRecord(ctx->ev_k1, st);
+    k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, 64), 64, 0, st>>>(pl, buckets, chunk_out);
+    k_msm_window_fold<<<1, 32, 0, st>>>(pl, chunk_out, windows);
+    k_msm_horner<<<1, 1, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
+    ctx->launches += 11;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+extern "C" {
+
+int schnorr_b200_batch_partial_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                                   const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                                   const uint8_t* rand32, uint8_t* partial192) {
+    if (!ctx || !partial192 || (n && (!sigs81 || !pk96 || !msg_off || !rand32))) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {  // empty slice: identity point, zero scalar
+        uint64_t h[24] = {0};
+        h[0] = 1;
+        h[6] = 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(partial192, h, 192, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return SCHNORR_B200_OK;
+    }
+    return batch_partial_impl(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, partial192);
+}
+
+int schnorr_b200_batch_finish_dev(schnorr_b200_ctx* ctx, size_t n_partials, const uint8_t* partials192,
+                                  uint8_t* result216) {
+    if (!ctx || !partials192 || !result216 || n_partials == 0) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    k_batch_finish<<<1, 1, 0, ctx->stream>>>(n_partials, (const uint64_t*)partials192, ctx->gtab, result216);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+static int read_result(schnorr_b200_ctx* ctx, const uint8_t* d_res, int* verdict, uint8_t* lhs97, uint8_t* rhs97) {
+    uint8_t h[RESULT_BYTES];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, d_res, RESULT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *verdict = h[0];
+    if (lhs97) memcpy(lhs97, h + 8, 97);
+    if (rhs97) memcpy(rhs97, h + 112, 97);
+    return SCHNORR_B200_OK;
+}
+
+int schnorr_b200_batch_finish(schnorr_b200_ctx* ctx, size_t n_partials, const uint8_t* partials192_host, int* verdict,
+                              uint8_t* lhs97, uint8_t* rhs97) {
+    if (!ctx || !partials192_host || !verdict || n_partials == 0) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_p, *d_res;
+    if (int rc = stage_in(ctx, SL_H, partials192_host, n_partials * 192, &d_p)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192, &d_res)) return rc;
+    uint8_t* res = (uint8_t*)d_res + 64;
+    if (int rc = schnorr_b200_batch_finish_dev(ctx, n_partials, (uint8_t*)d_p, res)) return rc;
+    return read_result(ctx, res, verdict, lhs97, rhs97);
+}
+
+int schnorr_b200_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
+                              int* verdict, uint8_t* lhs97, uint8_t* rhs97) {
+    if (!ctx || !verdict || (n && (!sigs81 || !pk96 || !msg_off || !rand32))) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* d_res;
+    if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192, &d_res)) return rc;
+    uint8_t* res = (uint8_t*)d_res + 64;
+    uint8_t* partial = res + RESULT_BYTES;
+    if (n == 0) {
+        if (int rc = schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial))
+            return rc;
+    } else {
+        size_t mb = msg_off[n];
+        if (mb && !msgs) return SCHNORR_B200_EARG;
+        // staging slots distinct from those batch_partial_impl uses (A-G, J-L): reuse H/I plus the
+        // tail of dedicated buffers allocated here
+        void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_rand;
+        size_t sz_sig = (n * 81 + 255) & ~(size_t)255, sz_pk = (n * 96 + 255) & ~(size_t)255,
+               sz_m = (mb + 255) & ~(size_t)255, sz_off = ((n + 1) * 8 + 255) & ~(size_t)255,
+               sz_rand = (n * 32 + 255) & ~(size_t)255, sz_inf = (n + 255) & ~(size_t)255;
+        void* blob;
+        if (int rc = ensure_scratch(ctx, SL_H, sz_sig + sz_pk + sz_m + sz_off + sz_rand + sz_inf, &blob)) return rc;
+        uint8_t* p = (uint8_t*)blob;
+        d_sig = p; p += sz_sig;
+        d_pk = p; p += sz_pk;
+        d_m = p; p += sz_m;
+        d_off = p; p += sz_off;
+        d_rand = p; p += sz_rand;
+        if (pk_inf) d_inf = p;
+        cudaStream_t st = ctx->stream;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_sig, sigs81, n * 81, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_pk, pk96, n * 96, cudaMemcpyHostToDevice, st));
+        if (mb) CUDA_TRY(ctx, cudaMemcpyAsync(d_m, msgs, mb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_rand, rand32, n * 32, cudaMemcpyHostToDevice, st));
+        if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(d_inf, pk_inf, n, cudaMemcpyHostToDevice, st));
+        if (int rc = batch_partial_impl(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
+                                        (uint64_t*)d_off, (uint8_t*)d_rand, partial))
+            return rc;
+    }
+    if (int rc = schnorr_b200_batch_finish_dev(ctx, 1, partial, res)) return rc;
+    return read_result(ctx, res, verdict, lhs97, rhs97);
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+// Cheetah curve  y^2 = x^3 + x + (u + 395)  over Fp6 (reference README.md:4-8; `cheetah::AffinePoint`
+// / `ProjectivePoint`, call sites src/signature.rs:182,196-200, src/batch.rs:98-123).
+//
+// Jacobian coordinates (X, Y, Z), x = X/Z^2, y = Y/Z^3, identity <=> Z = 0.  The verification
+// result is compared through its affine x only (src/signature.rs:200), so any algorithm producing
+// the same group element is bit-exact after normalisation.
+//
+// All formulas are branch-free on the common path; the exceptional inputs (identity operands,
+// P + P, P + (-P)) are handled exactly, because adversarial public keys of small order DO reach
+// them (the reference's own test uses an off-subgroup key, src/signature.rs:385-406).
+#pragma once
+#include "fp6.cuh"
+#include "scalar.cuh"
+
+namespace sb {
+
+struct jac_pt {
+    fp6 X, Y, Z;
+};
+struct aff_pt {
+    fp6 x, y;  // identity is carried out of band (table entries are never the identity)
+};
+
+SB_DEV jac_pt jac_identity() { return jac_pt{fp6_one(), fp6_one(), fp6_zero()}; }
+SB_DEV bool jac_is_identity(const jac_pt& p) { return fp6_is_zero(p.Z); }
+SB_DEV jac_pt jac_from_affine(const fp6& x, const fp6& y, bool inf) {
+    jac_pt r{x, y, fp6_one()};
+    if (inf) r = jac_identity();
+    return r;
+}
+SB_DEV jac_pt jac_neg(const jac_pt& p) { return jac_pt{p.X, fp6_neg(p.Y), p.Z}; }
+SB_DEV jac_pt jac_select(bool pick_b, const jac_pt& a, const jac_pt& b) {
+    return jac_pt{fp6_select(pick_b, a.X, b.X), fp6_select(pick_b, a.Y, b.Y), fp6_select(pick_b, a.Z, b.Z)};
+}
+
+// dbl-2007-bl with a = 1: 1M + 8S.  Complete: Z = 0 or Y = 0 (order-2 point) both give Z3 = 0.
+SB_DEV jac_pt jac_dbl(const jac_pt& p) {
+    fp6 XX = fp6_sqr(p.X);
+    fp6 YY = fp6_sqr(p.Y);
+    fp6 YYYY = fp6_sqr(YY);
+    fp6 ZZ = fp6_sqr(p.Z);
+    fp6 t = fp6_sqr(fp6_add(p.X, YY));
+    fp6 S = fp6_dbl(fp6_sub(fp6_sub(t, XX), YYYY));
+    fp6 M = fp6_add(fp6_add(fp6_dbl(XX), XX), fp6_sqr(ZZ));
+    jac_pt r;
+    r.X = fp6_sub(fp6_sqr(M), fp6_dbl(S));
+    fp6 y8 = fp6_dbl(fp6_dbl(fp6_dbl(YYYY)));
+    r.Y = fp6_sub(fp6_mul(M, fp6_sub(S, r.X)), y8);
+    r.Z = fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Y, p.Z)), YY), ZZ);
+    return r;
+}
+
+// add-2007-bl: 11M + 5S, with exact handling of identity operands and of P1 == +-P2.
+SB_DEV jac_pt jac_add(const jac_pt& p, const jac_pt& q) {
+    fp6 Z1Z1 = fp6_sqr(p.Z);
+    fp6 Z2Z2 = fp6_sqr(q.Z);
+    fp6 U1 = fp6_mul(p.X, Z2Z2);
+    fp6 U2 = fp6_mul(q.X, Z1Z1);
+    fp6 S1 = fp6_mul(fp6_mul(p.Y, q.Z), Z2Z2);
+    fp6 S2 = fp6_mul(fp6_mul(q.Y, p.Z), Z1Z1);
+    fp6 H = fp6_sub(U2, U1);
+    fp6 rr = fp6_sub(S2, S1);
+    bool p_inf = fp6_is_zero(p.Z), q_inf = fp6_is_zero(q.Z);
+    if (!p_inf && !q_inf && fp6_is_zero(H) && fp6_is_zero(rr)) return jac_dbl(p);  // rare: P1 == P2
+    fp6 I = fp6_sqr(fp6_dbl(H));
+    fp6 J = fp6_mul(H, I);
+    fp6 r2 = fp6_dbl(rr);
+    fp6 V = fp6_mul(U1, I);
+    jac_pt r;
+    r.X = fp6_sub(fp6_sub(fp6_sqr(r2), J), fp6_dbl(V));
+    r.Y = fp6_sub(fp6_mul(r2, fp6_sub(V, r.X)), fp6_dbl(fp6_mul(S1, J)));
+    r.Z = fp6_mul(fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);  // H = 0, rr != 0 -> identity
+    r = jac_select(q_inf, r, p);
+    r = jac_select(p_inf, r, q);
+    return r;
+}
+
+// madd-2007-bl (q affine, never the identity unless q_inf): 7M + 4S
+SB_DEV jac_pt jac_madd(const jac_pt& p, const fp6& qx, const fp6& qy, bool q_inf) {
+    fp6 Z1Z1 = fp6_sqr(p.Z);
+    fp6 U2 = fp6_mul(qx, Z1Z1);
+    fp6 S2 = fp6_mul(fp6_mul(qy, p.Z), Z1Z1);
+    fp6 H = fp6_sub(U2, p.X);
+    fp6 rr = fp6_sub(S2, p.Y);
+    bool p_inf = fp6_is_zero(p.Z);
+    if (!p_inf && !q_inf && fp6_is_zero(H) && fp6_is_zero(rr)) return jac_dbl(p);  // rare: P1 == P2
+    fp6 HH = fp6_sqr(H);
+    fp6 I = fp6_dbl(fp6_dbl(HH));
+    fp6 J = fp6_mul(H, I);
+    fp6 r2 = fp6_dbl(rr);
+    fp6 V = fp6_mul(p.X, I);
+    jac_pt r;
+    r.X = fp6_sub(fp6_sub(fp6_sqr(r2), J), fp6_dbl(V));
+    r.Y = fp6_sub(fp6_mul(r2, fp6_sub(V, r.X)), fp6_dbl(fp6_mul(p.Y, J)));
+    r.Z = fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Z, H)), Z1Z1), HH);
+    r = jac_select(q_inf, r, p);
+    r = jac_select(p_inf, r, jac_from_affine(qx, qy, q_inf));
+    return r;
+}
+
+// affine x of a Jacobian point; the identity reads as x = 0
+SB_DEV fp6 jac_affine_x(const jac_pt& p) {
+    fp6 zi = fp6_inv(p.Z);  // 0 for the identity
+    return fp6_mul(p.X, fp6_sqr(zi));
+}
+SB_DEV void jac_to_affine(const jac_pt& p, fp6& x, fp6& y, bool& inf) {
+    inf = fp6_is_zero(p.Z);
+    fp6 zi = fp6_inv(p.Z);
+    fp6 zi2 = fp6_sqr(zi);
+    x = fp6_mul(p.X, zi2);
+    y = fp6_mul(p.Y, fp6_mul(zi2, zi));
+}
+// X == x * Z^2 without an inversion (final comparison of verify); identity compares equal to x = 0 only
+SB_DEV bool jac_x_equals(const jac_pt& p, const fp6& x) {
+    if (fp6_is_zero(p.Z)) return fp6_is_zero(x);
+    return fp6_eq(p.X, fp6_mul(x, fp6_sqr(p.Z)));
+}
+SB_DEV bool aff_on_curve(const fp6& x, const fp6& y) {
+    fp6 rhs = fp6_add(fp6_mul(fp6_sqr(x), x), x);
+    rhs.c[0] = fp_add(rhs.c[0], 395);
+    rhs.c[1] = fp_add(rhs.c[1], 1);
+    return fp6_eq(fp6_sqr(y), rhs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Odd-multiples table of a variable base:  T[k] = (2k+1) * P,  k = 0..7  (1 dbl + 7 add).
+// Shared by the subgroup check (width-5 NAF of the constant q) and by the regular signed-odd
+// window-4 recoding of the challenge scalar.
+SB_DEV void build_odd_table(jac_pt* T, const jac_pt& P) {
+    jac_pt P2 = jac_dbl(P);
+    T[0] = P;
+#pragma unroll 1
+    for (int k = 1; k < 8; k++) T[k] = jac_add(T[k - 1], P2);
+}
+
+#if defined(__CUDACC__)
+__constant__ int8_t c_q_wnaf5[256];  // CHEETAH_Q_WNAF5, filled at context creation
+#define SB_QWNAF(i) c_q_wnaf5[i]
+#else
+#define SB_QWNAF(i) CHEETAH_Q_WNAF5[i]
+#endif
+
+// AffinePoint::is_torsion_free (call site src/signature.rs:182): [q]P == O, evaluated along the
+// fixed width-5 NAF addition chain of q (uniform across the warp: digits are constants).
+SB_DEV bool torsion_free_with_table(const jac_pt* T) {
+    int top = 255;
+    while (SB_QWNAF(top) == 0) top--;
+    int d = SB_QWNAF(top);  // positive by construction
+    jac_pt acc = T[d >> 1];
+#pragma unroll 1
+    for (int i = top - 1; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        int di = SB_QWNAF(i);
+        if (di != 0) {  // warp-uniform branch
+            int idx = (di < 0 ? -di : di) >> 1;
+            jac_pt t = T[idx];
+            if (di < 0) t.Y = fp6_neg(t.Y);
+            acc = jac_add(acc, t);
+        }
+    }
+    return jac_is_identity(acc);
+}
+
+// Regular signed-odd recoding, window 4 (Joye-Tunstall): an ODD k < 2^255 becomes 64 odd digits
+// d_i in {+-1, +-3, ..., +-15} with k = sum d_i 16^i.  Digits are returned packed: bit 4 = sign,
+// bits 0..2 = table index (|d|-1)/2.
+SB_DEV void recode_odd_w4(const scalar& k, uint8_t* digits /*64*/) {
+    // d_i = (k mod 32) - 16; k = (k - d_i) / 16  <=>  with odd k: d_i = ((k >> 4i) & 31 | 1) ... evaluated
+    // incrementally on the bit string: t_i = bits[4i .. 4i+4] of the running value.
+    // Closed form for odd k: d_i = 2 * b_{i}' - 15 ... ; we use the simple carry-free identity
+    //   d_i = (w_i | 1) - 16 * (1 - c_i) ...  -> implemented as the textbook loop on a copy of k.
+    scalar v = k;
+#pragma unroll 1
+    for (int i = 0; i < 63; i++) {
+        int w = (int)(v.l[0] & 31);       // k mod 2^(w+1)
+        int d = w - 16;                   // odd, in [-15, 15]
+        // v = (v - d) >> 4 : v - d = v - w + 16; low 5 bits of v become 10000b then shift by 4
+        v.l[0] = (v.l[0] & ~31u) | 16u;
+#pragma unroll
+        for (int j = 0; j < 7; j++) v.l[j] = (v.l[j] >> 4) | (v.l[j + 1] << 28);
+        v.l[7] >>= 4;
+        int a = d < 0 ? -d : d;
+        digits[i] = (uint8_t)(((d < 0) ? 16 : 0) | (a >> 1));
+    }
+    int d = (int)(v.l[0] & 31);  // remaining value, odd, <= 15 for k < 2^255 + ...
+    digits[63] = (uint8_t)(d >> 1);
+}
+
+// h*P + e*G with the odd table of P and a byte-indexed fixed-base table of G:
+//   gtab[(i*256 + b)] = b * 256^i * G  (affine x||y as 12 u64; entry b = 0 unused).
+// h, e canonical scalars.  (multiply_double_with_basepoint_vartime, src/signature.rs:196-198.)
+SB_DEV jac_pt double_base_mul(const jac_pt* T, const scalar& h, const scalar& e, const uint64_t* __restrict__ gtab) {
+    // make the variable-base scalar odd: for even h use q - h (odd) and flip every digit's sign
+    bool flip = (h.l[0] & 1) == 0;
+    scalar k = flip ? sc_cond_sub_q(sc_neg(h)) : h;
+    if (sc_is_zero(h)) {  // q - 0 = q is not canonical; [q]P = O anyway: use k = q directly
+#pragma unroll
+        for (int i = 0; i < 8; i++) k.l[i] = SB_CONST_Q(i);
+    }
+    uint8_t dg[64];
+    recode_odd_w4(k, dg);
+    jac_pt acc = jac_identity();
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+#pragma unroll 1
+            for (int s = 0; s < 4; s++) acc = jac_dbl(acc);
+        }
+        jac_pt t = T[dg[i] & 7];
+        bool neg = ((dg[i] >> 4) & 1) != (flip ? 1 : 0);
+        if (neg) t.Y = fp6_neg(t.Y);
+        acc = jac_add(acc, t);
+    }
+    // fixed base: 32 byte-windows, no doublings
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        uint32_t b = (e.l[i >> 2] >> (8 * (i & 3))) & 0xff;
+        const uint64_t* ent = gtab + ((size_t)(i * 256 + (b ? b : 1))) * 12;
+        fp6 gx, gy;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            gx.c[c] = ent[c];
+            gy.c[c] = ent[6 + c];
+        }
+        acc = jac_madd(acc, gx, gy, b == 0);
+    }
+    return acc;
+}
+
+// k*G with the same byte table (BASEPOINT_TABLE * scalar: src/public.rs:29, src/signature.rs:67,116,
+// src/batch.rs:98-100)
+SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab) {
+    jac_pt acc = jac_identity();
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        uint32_t b = (k.l[i >> 2] >> (8 * (i & 3))) & 0xff;
+        const uint64_t* ent = gtab + ((size_t)(i * 256 + (b ? b : 1))) * 12;
+        fp6 gx, gy;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            gx.c[c] = ent[c];
+            gy.c[c] = ent[6 + c];
+        }
+        acc = jac_madd(acc, gx, gy, b == 0);
+    }
+    return acc;
+}
+
+// plain double-and-add k*P for table construction (not a hot path)
+SB_DEV jac_pt jac_mul_bits(const jac_pt& P, const scalar& k) {
+    jac_pt acc = jac_identity();
+#pragma unroll 1
+    for (int i = 255; i >= 0; i--) {
+        acc = jac_dbl(acc);
+        if ((k.l[i >> 5] >> (i & 31)) & 1) acc = jac_add(acc, P);
+    }
+    return acc;
+}
+
+// AffinePoint::from_compressed (src/batch.rs:104, src/public.rs:55): 48 bytes of x + flag byte
+// (bit 7 infinity, bit 6 "y is the lexicographically largest root", other bits must be 0).
+// x arrives already split into limbs; returns false when the record does not decode.
+SB_DEV bool decompress_point(const fp6& x, uint8_t flags, fp6& ox, fp6& oy, bool& inf) {
+    ox = fp6_zero();
+    oy = fp6_zero();
+    inf = true;
+    if (flags & 0x3f) return false;
+    if (!fp6_is_canonical(x)) return false;
+    bool f_inf = (flags >> 7) & 1, f_sign = (flags >> 6) & 1;
+    if (f_inf) return fp6_is_zero(x) && !f_sign;
+    fp6 rhs = fp6_add(fp6_mul(fp6_sqr(x), x), x);
+    rhs.c[0] = fp_add(rhs.c[0], 395);
+    rhs.c[1] = fp_add(rhs.c[1], 1);
+    fp6 y;
+    if (!fp6_sqrt(rhs, y)) return false;
+    if (fp6_lex_largest(y) != f_sign) y = fp6_neg(y);
+    ox = x;
+    oy = y;
+    inf = false;
+    return true;
+}
+// AffinePoint::to_compressed flag byte
+SB_DEV uint8_t compress_flags(const fp6& y, bool inf) { return inf ? 0x80 : (fp6_lex_largest(y) ? 0x40 : 0x00); }
+
+}  // namespace sb

@@ -1,0 +1,328 @@
+// Sextic extension Fp6 = Fp[u]/(u^6 - 7) (reference README.md:8; `cheetah::Fp6`, call sites
+// src/signature.rs:186,278-282, src/batch.rs:67).  Coefficients c0..c5, canonical.
+//
+// Multiplication: the wrap-around terms (i + j >= 6) use b pre-scaled by 7, so every output
+// coefficient is exactly six 64x64 products accumulated lazily in column accumulators and reduced
+// once (fp.cuh).  24 IMAD.WIDE per coefficient, 144 per multiplication, 84 per squaring.
+#pragma once
+#include "fp.cuh"
+
+namespace sb {
+
+struct fp6 {
+    fp_t c[6];
+};
+
+SB_DEV fp6 fp6_zero() { return fp6{{0, 0, 0, 0, 0, 0}}; }
+SB_DEV fp6 fp6_one() { return fp6{{1, 0, 0, 0, 0, 0}}; }
+SB_DEV fp6 fp6_add(const fp6& a, const fp6& b) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = fp_add(a.c[i], b.c[i]);
+    return r;
+}
+SB_DEV fp6 fp6_sub(const fp6& a, const fp6& b) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = fp_sub(a.c[i], b.c[i]);
+    return r;
+}
+SB_DEV fp6 fp6_neg(const fp6& a) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = fp_neg(a.c[i]);
+    return r;
+}
+SB_DEV fp6 fp6_dbl(const fp6& a) { return fp6_add(a, a); }
+SB_DEV bool fp6_is_zero(const fp6& a) { return (a.c[0] | a.c[1] | a.c[2] | a.c[3] | a.c[4] | a.c[5]) == 0; }
+SB_DEV bool fp6_eq(const fp6& a, const fp6& b) {
+    uint64_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) d |= a.c[i] ^ b.c[i];
+    return d == 0;
+}
+SB_DEV fp6 fp6_select(bool pick_b, const fp6& a, const fp6& b) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = pick_b ? b.c[i] : a.c[i];
+    return r;
+}
+// every limb canonical?  (Fp6::from_bytes is None otherwise -> the reference panics, src/signature.rs:186)
+SB_DEV bool fp6_is_canonical(const fp6& a) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 6; i++) ok &= a.c[i] < FP_P;
+    return ok;
+}
+
+SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
+    fp_t b7[6];
+#pragma unroll
+    for (int j = 1; j < 6; j++) b7[j] = fp_mul7(b.c[j]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        wide_acc w;
+        wide_zero(w);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            if (i <= k) wide_mac(w, a.c[i], b.c[k - i]);
+            else wide_mac(w, a.c[i], b7[k + 6 - i]);
+        }
+        r.c[k] = wide_reduce(w);
+    }
+}
+
+SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) {
+    fp_t a7[6];
+#pragma unroll
+    for (int j = 3; j < 6; j++) a7[j] = fp_mul7(a.c[j]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        wide_acc w;
+        wide_zero(w);
+        // cross terms i < j
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+#pragma unroll
+            for (int j = i + 1; j < 6; j++) {
+                if (i + j == k) wide_mac(w, a.c[i], a.c[j]);
+                if (i + j == k + 6) wide_mac(w, a.c[i], a7[j]);
+            }
+        }
+        wide_double(w);
+        if ((k & 1) == 0) {
+            wide_mac_sqr(w, a.c[k / 2]);
+            wide_mac(w, a.c[k / 2 + 3], a7[k / 2 + 3]);
+        }
+        r.c[k] = wide_reduce(w);
+    }
+}
+
+#ifndef SB_FP6_INLINE
+#define SB_FP6_INLINE 0
+#endif
+#if SB_FP6_INLINE
+SB_DEV fp6 fp6_mul(const fp6& a, const fp6& b) {
+    fp6 r;
+    fp6_mul_body(r, a, b);
+    return r;
+}
+SB_DEV fp6 fp6_sqr(const fp6& a) {
+    fp6 r;
+    fp6_sqr_body(r, a);
+    return r;
+}
+#else
+// Out-of-line: one copy of the ~500-instruction bodies per kernel keeps the hot loops inside the
+// instruction cache.
+SB_DEV_NOINLINE fp6 fp6_mul(fp6 a, fp6 b) {
+    fp6 r;
+    fp6_mul_body(r, a, b);
+    return r;
+}
+SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
+    fp6 r;
+    fp6_sqr_body(r, a);
+    return r;
+}
+#endif
+
+SB_DEV fp6 fp6_mul_small(const fp6& a, uint32_t k) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = fp_mul_small(a.c[i], k);
+    return r;
+}
+
+// ---- cubic subfield Fp3 = Fp[v]/(v^3 - 7), v = u^2, used by inversion and square roots ----
+struct fp3 {
+    fp_t c[3];
+};
+SB_DEV fp3 fp3_mul(const fp3& a, const fp3& b) {
+    fp3 r;
+    fp_t b7_1 = fp_mul7(b.c[1]), b7_2 = fp_mul7(b.c[2]);
+    wide_acc w;
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[0]);
+    wide_mac(w, a.c[1], b7_2);
+    wide_mac(w, a.c[2], b7_1);
+    r.c[0] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[1]);
+    wide_mac(w, a.c[1], b.c[0]);
+    wide_mac(w, a.c[2], b7_2);
+    r.c[1] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[2]);
+    wide_mac(w, a.c[1], b.c[1]);
+    wide_mac(w, a.c[2], b.c[0]);
+    r.c[2] = wide_reduce(w);
+    return r;
+}
+SB_DEV fp3 fp3_sqr(const fp3& a) { return fp3_mul(a, a); }
+SB_DEV fp3 fp3_sub(const fp3& a, const fp3& b) {
+    return fp3{{fp_sub(a.c[0], b.c[0]), fp_sub(a.c[1], b.c[1]), fp_sub(a.c[2], b.c[2])}};
+}
+SB_DEV fp3 fp3_add(const fp3& a, const fp3& b) {
+    return fp3{{fp_add(a.c[0], b.c[0]), fp_add(a.c[1], b.c[1]), fp_add(a.c[2], b.c[2])}};
+}
+SB_DEV fp3 fp3_neg(const fp3& a) { return fp3{{fp_neg(a.c[0]), fp_neg(a.c[1]), fp_neg(a.c[2])}}; }
+SB_DEV fp3 fp3_mulv(const fp3& a) { return fp3{{fp_mul7(a.c[2]), a.c[0], a.c[1]}}; }  // * v
+SB_DEV fp3 fp3_scale(const fp3& a, fp_t k) { return fp3{{fp_mul(a.c[0], k), fp_mul(a.c[1], k), fp_mul(a.c[2], k)}}; }
+SB_DEV bool fp3_is_zero(const fp3& a) { return (a.c[0] | a.c[1] | a.c[2]) == 0; }
+// adjugate / norm:  d^-1 = (t0 + t1 v + t2 v^2) / N(d)
+SB_DEV void fp3_adj_norm(const fp3& d, fp3& adj, fp_t& norm) {
+    fp_t d0 = d.c[0], d1 = d.c[1], d2 = d.c[2];
+    fp_t t0 = fp_sub(fp_sqr(d0), fp_mul7(fp_mul(d1, d2)));
+    fp_t t1 = fp_sub(fp_mul7(fp_sqr(d2)), fp_mul(d0, d1));
+    fp_t t2 = fp_sub(fp_sqr(d1), fp_mul(d0, d2));
+    norm = fp_add(fp_mul(d0, t0), fp_mul7(fp_add(fp_mul(d2, t1), fp_mul(d1, t2))));
+    adj = fp3{{t0, t1, t2}};
+}
+SB_DEV fp3 fp3_inv(const fp3& d) {
+    fp3 adj;
+    fp_t n;
+    fp3_adj_norm(d, adj, n);
+    return fp3_scale(adj, fp_inv(n));
+}
+SB_DEV void fp6_split(const fp6& a, fp3& a0, fp3& a1) {  // a = a0 + a1*u over Fp3
+    a0 = fp3{{a.c[0], a.c[2], a.c[4]}};
+    a1 = fp3{{a.c[1], a.c[3], a.c[5]}};
+}
+SB_DEV fp6 fp6_join(const fp3& a0, const fp3& a1) { return fp6{{a0.c[0], a1.c[0], a0.c[1], a1.c[1], a0.c[2], a1.c[2]}}; }
+
+// a^-1 through the tower Fp6 = Fp3[u]/(u^2 - v):  (a0 + a1 u)^-1 = (a0 - a1 u) / (a0^2 - v a1^2).
+// Returns 0 for a = 0.
+SB_DEV fp6 fp6_inv(const fp6& a) {
+    fp3 a0, a1;
+    fp6_split(a, a0, a1);
+    fp3 d = fp3_sub(fp3_sqr(a0), fp3_mulv(fp3_sqr(a1)));
+    fp3 di = fp3_inv(d);
+    return fp6_join(fp3_mul(a0, di), fp3_mul(fp3_neg(a1), di));
+}
+
+// "lexicographically largest": decided by the highest non-zero coefficient (oracle/pyref.py
+// f6_lex_largest; [RECALLED] convention of cheetah's compressed encoding)
+SB_DEV bool fp6_lex_largest(const fp6& a) {
+    bool res = false, decided = false;
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        bool nz = a.c[i] != 0;
+        bool big = a.c[i] > (FP_P - 1) / 2;
+        res = decided ? res : (nz & big);
+        decided |= nz;
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Square roots (used by AffinePoint::from_compressed: src/batch.rs:104, src/public.rs:55).
+// Which root is returned is irrelevant: the caller fixes the sign with the flag bit.
+
+// a^(2^32 - 1)
+SB_DEV fp_t fp_pow_2_32_m1(fp_t a) {
+    fp_t t2 = fp_mul(fp_sqr(a), a);
+    fp_t t4 = fp_mul(fp_sqr_n(t2, 2), t2);
+    fp_t t8 = fp_mul(fp_sqr_n(t4, 4), t4);
+    fp_t t16 = fp_mul(fp_sqr_n(t8, 8), t8);
+    return fp_mul(fp_sqr_n(t16, 16), t16);
+}
+// Legendre symbol: a^((p-1)/2) == 1 (a != 0);  (p-1)/2 = 2^31 * (2^32 - 1)
+SB_DEV bool fp_is_square(fp_t a) {
+    if (a == 0) return true;
+    return fp_sqr_n(fp_pow_2_32_m1(a), 31) == 1;
+}
+// Tonelli-Shanks in Fp: p - 1 = 2^32 * (2^32 - 1).  Returns false if a is not a square.
+SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
+    if (a == 0) {
+        out = 0;
+        return true;
+    }
+    fp_t x = fp_sqr_n(a, 31);        // a^((t+1)/2), t = 2^32 - 1
+    fp_t b = fp_pow_2_32_m1(a);      // a^t
+    fp_t g = 0x185629dcda58878cULL;  // FP_ROOT_OF_UNITY_2_32 = 7^t (include/cheetah_params.h)
+    int r = 32;
+    while (b != 1) {
+        int m = 0;
+        fp_t bb = b;
+        while (bb != 1) {
+            bb = fp_sqr(bb);
+            if (++m == r) return false;
+        }
+        fp_t gs = fp_sqr_n(g, r - m - 1);
+        g = fp_sqr(gs);
+        x = fp_mul(x, gs);
+        b = fp_mul(b, g);
+        r = m;
+    }
+    out = x;
+    return true;
+}
+
+SB_DEV fp3 fp3_sqr_n(fp3 a, int n) {
+    for (int i = 0; i < n; i++) a = fp3_sqr(a);
+    return a;
+}
+SB_DEV fp_t fp3_norm(const fp3& a) {
+    fp3 adj;
+    fp_t n;
+    fp3_adj_norm(a, adj, n);
+    return n;
+}
+// a is a square in Fp3  <=>  N(a) is a square in Fp  (odd-degree extension)
+SB_DEV bool fp3_is_square(const fp3& a) { return fp_is_square(fp3_norm(a)); }
+// sqrt in Fp3 through the norm: with e = p^2 + p + 1 (odd), a^e = N(a) in Fp and
+//   sqrt(a) = a^((e+1)/2) / sqrt(N(a)),   a^((e+1)/2) = Frob(a^((p+1)/2)) * a,  (p+1)/2 = 2^31 (2^32-1) + 1
+SB_DEV bool fp3_sqrt(const fp3& a, fp3& out) {
+    if (fp3_is_zero(a)) {
+        out = a;
+        return true;
+    }
+    fp_t s;
+    if (!fp_sqrt(fp3_norm(a), s)) return false;
+    // c = a^(2^32 - 1)
+    fp3 t2 = fp3_mul(fp3_sqr(a), a);
+    fp3 t4 = fp3_mul(fp3_sqr_n(t2, 2), t2);
+    fp3 t8 = fp3_mul(fp3_sqr_n(t4, 4), t4);
+    fp3 t16 = fp3_mul(fp3_sqr_n(t8, 8), t8);
+    fp3 c = fp3_mul(fp3_sqr_n(t16, 16), t16);
+    c = fp3_mul(fp3_sqr_n(c, 31), a);  // a^((p+1)/2)
+    const fp_t w = 0xfffffffe00000001ULL;  // FP_OMEGA3: v^p = w v
+    const fp_t w2 = fp_sqr(w);
+    fp3 f = fp3{{c.c[0], fp_mul(c.c[1], w), fp_mul(c.c[2], w2)}};  // Frobenius
+    out = fp3_scale(fp3_mul(f, a), fp_inv(s));
+    return true;
+}
+
+// sqrt in Fp6 = Fp3[u]/(u^2 - v) by the complex method.  Returns false if a is not a square.
+SB_DEV bool fp6_sqrt(const fp6& a, fp6& out) {
+    fp3 a0, a1;
+    fp6_split(a, a0, a1);
+    const fp_t half = 0x7fffffff80000001ULL;  // 2^-1 mod p
+    if (fp3_is_zero(a1)) {
+        // a in Fp3: a square there, or v * square (then the root is a multiple of u)
+        fp3 r;
+        if (fp3_sqrt(a0, r)) {
+            out = fp6_join(r, fp3{{0, 0, 0}});
+            return true;
+        }
+        // a0 / v = (c1, c2, c0/7): sqrt(a0) = sqrt(a0/v) * u
+        const fp_t inv7 = 0x249249246db6db6eULL;  // 7^-1 mod p
+        fp3 q = fp3{{a0.c[1], a0.c[2], fp_mul(a0.c[0], inv7)}};
+        if (!fp3_sqrt(q, r)) return false;  // cannot happen
+        out = fp6_join(fp3{{0, 0, 0}}, r);
+        return true;
+    }
+    fp3 nrm = fp3_sub(fp3_sqr(a0), fp3_mulv(fp3_sqr(a1)));
+    fp3 n;
+    if (!fp3_sqrt(nrm, n)) return false;
+    fp3 d = fp3_scale(fp3_add(a0, n), half);
+    if (!fp3_is_square(d)) d = fp3_scale(fp3_sub(a0, n), half);
+    fp3 x0;
+    if (!fp3_sqrt(d, x0)) return false;
+    fp3 x1 = fp3_mul(a1, fp3_inv(fp3_add(x0, x0)));
+    out = fp6_join(x0, x1);
+    return fp6_eq(fp6_sqr(out), a);
+}
+
+}  // namespace sb

@@ -1,0 +1,149 @@
+// Rescue-Prime over Goldilocks, state 12 / rate 8 / capacity 4 -- the `hash::rescue_64_12_8::RescueHash`
+// the reference calls at src/signature.rs:303-305 -- and the reference's own `hash_message`
+// (src/signature.rs:274-306).  Instance parameters: include/cheetah_params.h (provenance in
+// params/params.json; rounds/MDS/padding are "parity unpinned").
+//
+// One message per thread; the 12-element state lives in registers; the circulant MDS row and the
+// 168 round constants sit in __constant__ memory (uniform across the warp -> constant-cache
+// broadcast, no shared-memory staging needed).
+#pragma once
+#include "../../include/cheetah_params.h"
+#include "fp6.cuh"
+#include "scalar.cuh"
+
+namespace sb {
+
+// circulant first row (RESCUE_MDS_ROW) and round constants (RESCUE_ARK) of cheetah_params.h
+SB_CONSTANT uint32_t c_mds_row[12] = {7, 23, 8, 26, 13, 10, 9, 7, 6, 22, 21, 8};
+#if defined(__CUDACC__)
+__constant__ uint64_t c_ark[2 * RESCUE_ROUNDS * 12];  // filled from RESCUE_ARK at context creation
+#define SB_ARK(i) c_ark[i]
+#else
+#define SB_ARK(i) RESCUE_ARK[i]
+#endif
+
+// x^7
+SB_DEV fp_t rescue_sbox(fp_t x) {
+    fp_t x2 = fp_sqr(x);
+    fp_t x3 = fp_mul(x2, x);
+    fp_t x4 = fp_sqr(x2);
+    return fp_mul(x3, x4);
+}
+
+// y = M * s + k  with M circulant, entries <= 26: the low and high 32-bit halves of the inputs are
+// accumulated separately in 64-bit registers (12 * 26 * 2^32 < 2^41: no carries), one reduction per output.
+SB_DEV void rescue_mds_ark(fp_t* s, int ark_row) {
+    fp_t t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) {
+            uint32_t m = c_mds_row[(j - i + 12) % 12];
+            lo += (uint64_t)(uint32_t)s[j] * m;
+            hi += (s[j] >> 32) * m;
+        }
+        // value = lo + hi * 2^32 < 2^74
+        uint64_t mid = (lo >> 32) + hi;  // weight 2^32, < 2^43
+        fp_t r = fp_reduce160((uint32_t)lo, (uint32_t)mid, (uint32_t)(mid >> 32), 0, 0);
+        t[i] = fp_add(r, SB_ARK(ark_row * 12 + i));
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = t[i];
+}
+
+// x^(1/7) = x^0x92492491b6db6db7: sliding pattern "100" x 10, then "110" x 10 + "111":
+// 63 squarings + 9 multiplications.
+SB_DEV fp_t rescue_inv_sbox(fp_t x) {
+    fp_t t1 = fp_sqr(x);                          // 10b
+    fp_t t2 = fp_sqr(t1);                         // 100b
+    fp_t t3 = fp_mul(fp_sqr_n(t2, 3), t2);        // 100100b
+    fp_t t4 = fp_mul(fp_sqr_n(t3, 6), t3);        // (100)x4
+    fp_t t5 = fp_mul(fp_sqr_n(t4, 12), t4);       // (100)x8
+    fp_t t6 = fp_mul(fp_sqr_n(t5, 6), t3);        // (100)x10
+    fp_t t7 = fp_mul(fp_sqr_n(t6, 31), t6);       // (100)x10 0 (100)x10
+    fp_t a = fp_sqr_n(fp_mul(fp_sqr(t7), t6), 2);
+    fp_t b = fp_mul(fp_mul(t1, t2), x);           // x^7
+    return fp_mul(a, b);
+}
+
+SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
+#pragma unroll 1
+    for (int r = 0; r < RESCUE_ROUNDS; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = rescue_sbox(s[i]);
+        rescue_mds_ark(s, 2 * r);
+        // inverse S-box, 4 independent chains at a time for ILP without blowing up registers
+#pragma unroll 1
+        for (int g = 0; g < 12; g += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[g + i] = rescue_inv_sbox(s[g + i]);
+        }
+        rescue_mds_ark(s, 2 * r + 1);
+    }
+}
+
+// Streaming sponge = RescueHash::hash_field: additive absorption into state[0..8], permutation per
+// full block, a single '1' element of padding only when the last block is partial, digest = state[0..4].
+struct rescue_sponge {
+    fp_t s[12];
+    int i;
+};
+SB_DEV void sponge_init(rescue_sponge& sp) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) sp.s[k] = 0;
+    sp.i = 0;
+}
+SB_DEV void sponge_absorb(rescue_sponge& sp, fp_t e) {
+    // dynamic index into a register array would spill: select statically
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (k == sp.i) sp.s[k] = fp_add(sp.s[k], e);
+    if (++sp.i == 8) {
+        rescue_permutation(sp.s);
+        sp.i = 0;
+    }
+}
+SB_DEV void sponge_finish(rescue_sponge& sp) {
+    if (sp.i > 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k == sp.i) sp.s[k] = fp_add(sp.s[k], 1);
+        rescue_permutation(sp.s);
+    }
+}
+
+// load up to 7 message bytes as a little-endian integer
+SB_DEV uint64_t load_le_bytes(const uint8_t* p, int n) {
+    uint64_t v = 0;
+    for (int k = 0; k < n; k++) v |= (uint64_t)p[k] << (8 * k);
+    return v;
+}
+
+// hash_message (src/signature.rs:274-306): absorb R.x (6), P.x (6), P.y[0] (1), then the message in
+// 7-byte little-endian chunks; a short tail chunk gets a 0x01 marker byte after its last byte.
+// Returns the digest as 4 field elements (Digest::to_bytes = their little-endian bytes).
+SB_DEV void hash_message(const fp6& rx, const fp6& px, fp_t py0, const uint8_t* msg, uint64_t len, fp_t* digest) {
+    rescue_sponge sp;
+    sponge_init(sp);
+    // first block is always full: 8 of the 13 fixed elements
+    sp.s[0] = rx.c[0]; sp.s[1] = rx.c[1]; sp.s[2] = rx.c[2]; sp.s[3] = rx.c[3];
+    sp.s[4] = rx.c[4]; sp.s[5] = rx.c[5]; sp.s[6] = px.c[0]; sp.s[7] = px.c[1];
+    rescue_permutation(sp.s);
+    sp.s[0] = fp_add(sp.s[0], px.c[2]); sp.s[1] = fp_add(sp.s[1], px.c[3]);
+    sp.s[2] = fp_add(sp.s[2], px.c[4]); sp.s[3] = fp_add(sp.s[3], px.c[5]);
+    sp.s[4] = fp_add(sp.s[4], py0);
+    sp.i = 5;
+    uint64_t nb = len / 7;
+    for (uint64_t c = 0; c < nb; c++) sponge_absorb(sp, load_le_bytes(msg + 7 * c, 7));
+    int rem = (int)(len - 7 * nb);
+    if (rem) sponge_absorb(sp, load_le_bytes(msg + 7 * nb, rem) | (1ULL << (8 * rem)));
+    sponge_finish(sp);
+#pragma unroll
+    for (int k = 0; k < 4; k++) digest[k] = sp.s[k];
+}
+
+// digest (4 canonical field elements, little-endian) -> Scalar::from_bits_vartime = integer mod q
+SB_DEV scalar digest_to_scalar(const fp_t* d) { return sc_from_u256(sc_from_u64x4(d[0], d[1], d[2], d[3])); }
+
+}  // namespace sb

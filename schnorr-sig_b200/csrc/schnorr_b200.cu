@@ -1,0 +1,684 @@
+// schnorr_b200 -- kernels, host orchestration and the C ABI (include/schnorr_b200.h).
+//
+// Kernel inventory ("kernels the new build must create"):
+//   k_ingest          AoS wire records -> SoA limb planes (coalesced 128-bit stores), input checks
+//   k_hash            K1  hash_message per thread
+//   k_verify          K2  Signature::verify per thread (challenge hash + subgroup check + h*P + e*G)
+//   k_keygen / k_sign K5  fixed-base multiplication; device signer for synthetic inputs
+//   k_gtab_*              builds the fixed-base table of G at context creation
+//   k_imad_peak       K6  integer-multiply roofline calibration
+//   batch kernels     K3/K4  in batch.cuh (Pippenger MSM)
+// No CPU fallback exists: every entry point needs a live CUDA context.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cheetah_params.h"
+#include "../../include/schnorr_b200.h"
+#include "verify.cuh"
+
+using namespace sb;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static constexpr int GTAB_WINDOWS = 32;
+static constexpr int GTAB_ENTRIES = 256;
+static constexpr size_t GTAB_U64 = (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 12;
+
+enum scratch_slot { SL_A = 0, SL_B, SL_C, SL_D, SL_E, SL_F, SL_G, SL_H, SL_I, SL_J, SL_K, SL_L, SL_COUNT };
+
+struct schnorr_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    uint64_t* gtab = nullptr;
+    void* scratch[SL_COUNT] = {};
+    size_t scratch_cap[SL_COUNT] = {};
+    uint64_t launches = 0;
+    int sm_count = 148;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
+    std::string err;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
+            return SCHNORR_B200_ECUDA;                                                           \
+        }                                                                                        \
+    } while (0)
+
+static int ensure_scratch(schnorr_b200_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_cap[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_cap[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 8;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->scratch[slot], cap));
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SoA device layout: plane-major ulonglong2, plane p of an Fp6 holds coefficients (2p, 2p+1).
+//   sx[3][n] sig.x   se[2][n] sig.e   px[3][n] py[3][n] public key   fl[n] flags
+// A warp reads 32 x 16 B = 512 contiguous bytes per plane.
+// ------------------------------------------------------------------------------------------------
+static constexpr uint8_t FL_PK_INF = 1;     // public key is the identity
+static constexpr uint8_t FL_X_BAD = 2;      // sig.x has a non-canonical limb
+static constexpr uint8_t FL_MALFORMED = 4;  // e >= q or non-canonical public-key limb
+static constexpr int SOA_PLANES = 11;
+
+struct soa_batch {
+    ulonglong2* planes;  // [11][n]: 0-2 sx, 3-4 se, 5-7 px, 8-10 py
+    uint8_t* flags;      // [n]
+    uint8_t* sig_flag;   // [n] byte 48 of the compressed point (used by batch verification only)
+    size_t n;
+};
+
+__device__ __forceinline__ fp6 load_fp6_planes(const ulonglong2* planes, int first_plane, size_t n, size_t i) {
+    ulonglong2 a = planes[(size_t)(first_plane + 0) * n + i];
+    ulonglong2 b = planes[(size_t)(first_plane + 1) * n + i];
+    ulonglong2 c = planes[(size_t)(first_plane + 2) * n + i];
+    return fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
+}
+__device__ __forceinline__ scalar load_scalar_planes(const ulonglong2* planes, int first_plane, size_t n, size_t i) {
+    ulonglong2 a = planes[(size_t)(first_plane + 0) * n + i];
+    ulonglong2 b = planes[(size_t)(first_plane + 1) * n + i];
+    return sc_from_u64x4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+    return v;
+}
+
+// AoS -> SoA.  The 81-byte signature records of a block are staged through shared memory with
+// coalesced 16-byte loads; public keys (96 B, 8-byte aligned) are read directly.
+static constexpr int INGEST_THREADS = 128;
+__global__ void __launch_bounds__(INGEST_THREADS) k_ingest(size_t n, const uint8_t* __restrict__ sigs81,
+                                                           const uint8_t* __restrict__ pk96,
+                                                           const uint8_t* __restrict__ pk_inf, soa_batch out) {
+    __shared__ __align__(16) uint8_t s_sig[INGEST_THREADS * 81];
+    size_t base = (size_t)blockIdx.x * INGEST_THREADS;
+    size_t cnt = n - base < (size_t)INGEST_THREADS ? n - base : (size_t)INGEST_THREADS;
+    size_t bytes = cnt * 81;
+    const uint8_t* src = sigs81 + base * 81;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        size_t nv = bytes / 16;
+        for (size_t k = threadIdx.x; k < nv; k += INGEST_THREADS)
+            reinterpret_cast<uint4*>(s_sig)[k] = reinterpret_cast<const uint4*>(src)[k];
+        for (size_t k = nv * 16 + threadIdx.x; k < bytes; k += INGEST_THREADS) s_sig[k] = src[k];
+    } else {
+        for (size_t k = threadIdx.x; k < bytes; k += INGEST_THREADS) s_sig[k] = src[k];
+    }
+    __syncthreads();
+    size_t i = base + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* rec = s_sig + threadIdx.x * 81;
+    uint64_t x[6], e[4];
+#pragma unroll
+    for (int k = 0; k < 6; k++) x[k] = load_u64_le(rec + 8 * k);
+#pragma unroll
+    for (int k = 0; k < 4; k++) e[k] = load_u64_le(rec + 49 + 8 * k);
+    const uint64_t* pk = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    uint64_t p[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) p[k] = pk[k];
+    uint8_t fl = 0;
+    bool inf = pk_inf != nullptr && pk_inf[i] != 0;
+    if (inf) fl |= FL_PK_INF;
+    bool x_ok = true, pk_ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++) x_ok &= x[k] < FP_P;
+#pragma unroll
+    for (int k = 0; k < 12; k++) pk_ok &= p[k] < FP_P;
+    if (!x_ok) fl |= FL_X_BAD;
+    if ((!pk_ok && !inf) || sc_geq_q(sc_from_u64x4(e[0], e[1], e[2], e[3]))) fl |= FL_MALFORMED;
+    size_t N = out.n;
+    ulonglong2* pl = out.planes;
+    pl[0 * N + i] = make_ulonglong2(x[0], x[1]);
+    pl[1 * N + i] = make_ulonglong2(x[2], x[3]);
+    pl[2 * N + i] = make_ulonglong2(x[4], x[5]);
+    pl[3 * N + i] = make_ulonglong2(e[0], e[1]);
+    pl[4 * N + i] = make_ulonglong2(e[2], e[3]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) pl[(size_t)(5 + k) * N + i] = make_ulonglong2(p[2 * k], p[2 * k + 1]);
+    out.flags[i] = fl;
+    out.sig_flag[i] = rec[48];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: Signature::verify, one signature per thread
+// ------------------------------------------------------------------------------------------------
+static constexpr int VERIFY_THREADS = 128;
+__global__ void __launch_bounds__(VERIFY_THREADS) k_verify(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                           const uint64_t* __restrict__ msg_off,
+                                                           const uint64_t* __restrict__ gtab,
+                                                           uint8_t* __restrict__ verdicts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    uint8_t fl = in.flags[i];
+    if (fl & FL_MALFORMED) {
+        verdicts[i] = VERDICT_MALFORMED;
+        return;
+    }
+    fp6 sx = load_fp6_planes(in.planes, 0, in.n, i);
+    scalar e = load_scalar_planes(in.planes, 3, in.n, i);
+    fp6 px = load_fp6_planes(in.planes, 5, in.n, i);
+    fp6 py = load_fp6_planes(in.planes, 8, in.n, i);
+    bool pk_inf = fl & FL_PK_INF;
+    bool x_ok = !(fl & FL_X_BAD);
+    uint64_t off = msg_off[i];
+    scalar h = sc_zero();
+    if (x_ok) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+    verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: hash_message, one message per thread (AoS inputs: 8-byte aligned records)
+// ------------------------------------------------------------------------------------------------
+static constexpr int HASH_THREADS = 128;
+__global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* __restrict__ rx48,
+                                                       const uint8_t* __restrict__ pk96,
+                                                       const uint8_t* __restrict__ msgs,
+                                                       const uint64_t* __restrict__ msg_off,
+                                                       uint8_t* __restrict__ digests) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* r = reinterpret_cast<const uint64_t*>(rx48 + i * 48);
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    fp6 rx, px;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        rx.c[k] = r[k];
+        px.c[k] = p[k];
+    }
+    fp_t py0 = p[6];
+    fp_t d[4];
+    uint64_t off = msg_off[i];
+    hash_message(rx, px, py0, msgs + off, msg_off[i + 1] - off, d);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + i * 32);
+    o[0] = make_ulonglong2(d[0], d[1]);
+    o[1] = make_ulonglong2(d[2], d[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: fixed-base multiplication -> key generation and the device signer
+// ------------------------------------------------------------------------------------------------
+static constexpr int SIGN_THREADS = 128;
+__device__ __forceinline__ void store_point96(uint8_t* dst, const fp6& x, const fp6& y) {
+    uint64_t* o = reinterpret_cast<uint64_t*>(dst);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        o[k] = x.c[k];
+        o[6 + k] = y.c[k];
+    }
+}
+__global__ void __launch_bounds__(SIGN_THREADS) k_keygen(size_t n, const uint8_t* __restrict__ sk32,
+                                                         const uint64_t* __restrict__ gtab, uint8_t* __restrict__ pk96,
+                                                         uint8_t* __restrict__ pk_inf) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    scalar k = sc_from_u256(sc_load_le(sk32 + 32 * i));
+    jac_pt P = fixed_base_mul(k, gtab);
+    fp6 x, y;
+    bool inf;
+    jac_to_affine(P, x, y, inf);
+    store_point96(pk96 + 96 * i, x, y);
+    if (pk_inf) pk_inf[i] = inf ? 1 : 0;
+}
+__global__ void __launch_bounds__(SIGN_THREADS) k_sign(size_t n, const uint8_t* __restrict__ sk32,
+                                                       const uint8_t* __restrict__ pk96,
+                                                       const uint8_t* __restrict__ pk_inf,
+                                                       const uint8_t* __restrict__ msgs,
+                                                       const uint64_t* __restrict__ msg_off,
+                                                       const uint8_t* __restrict__ nonce32,
+                                                       const uint64_t* __restrict__ gtab, uint8_t* __restrict__ sigs81) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    scalar sk = sc_from_u256(sc_load_le(sk32 + 32 * i));
+    scalar r = sc_from_u256(sc_load_le(nonce32 + 32 * i));
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    fp6 px, py;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        px.c[k] = p[k];
+        py.c[k] = p[6 + k];
+    }
+    bool inf = pk_inf != nullptr && pk_inf[i] != 0;
+    jac_pt R = fixed_base_mul(r, gtab);
+    fp6 x, y;
+    bool r_inf;
+    jac_to_affine(R, x, y, r_inf);  // identity -> x = y = 0
+    uint64_t off = msg_off[i];
+    scalar h = challenge_scalar(x, px, py, inf, msgs + off, msg_off[i + 1] - off);
+    scalar e = sc_sub(r, sc_mul(sk, h));
+    uint8_t* o = sigs81 + 81 * i;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) o[8 * k + b] = (uint8_t)(x.c[k] >> (8 * b));
+    o[48] = compress_flags(y, r_inf);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) o[49 + 4 * k + b] = (uint8_t)(e.l[k] >> (8 * b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// compressed point codecs (PublicKey::from_bytes / to_bytes, src/public.rs:49-56)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_decompress(size_t n, const uint8_t* __restrict__ in49, uint8_t* __restrict__ pk96,
+                                                    uint8_t* __restrict__ pk_inf, uint8_t* __restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* rec = in49 + 49 * i;
+    fp6 x;
+#pragma unroll
+    for (int k = 0; k < 6; k++) x.c[k] = load_u64_le(rec + 8 * k);
+    fp6 ox, oy;
+    bool inf;
+    bool good = decompress_point(x, rec[48], ox, oy, inf);
+    store_point96(pk96 + 96 * i, ox, oy);
+    pk_inf[i] = inf ? 1 : 0;
+    ok[i] = good ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_compress(size_t n, const uint8_t* __restrict__ pk96,
+                                                  const uint8_t* __restrict__ pk_inf, uint8_t* __restrict__ out49) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    bool inf = pk_inf != nullptr && pk_inf[i] != 0;
+    fp6 y;
+#pragma unroll
+    for (int k = 0; k < 6; k++) y.c[k] = p[6 + k];
+    uint8_t* o = out49 + 49 * i;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint64_t v = inf ? 0 : p[k];
+#pragma unroll
+        for (int b = 0; b < 8; b++) o[8 * k + b] = (uint8_t)(v >> (8 * b));
+    }
+    o[48] = compress_flags(y, inf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-base table of G:  gtab[i][b] = b * 256^i * G  (affine), i < 32, 1 <= b < 256
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gtab_bases(jac_pt* bases, fp6 gx, fp6 gy) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= GTAB_WINDOWS) return;
+    jac_pt p = jac_from_affine(gx, gy, false);
+    for (int k = 0; k < 8 * i; k++) p = jac_dbl(p);
+    bases[i] = p;
+}
+__global__ void __launch_bounds__(128) k_gtab_fill(const jac_pt* __restrict__ bases, uint64_t* __restrict__ gtab) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= GTAB_WINDOWS * GTAB_ENTRIES) return;
+    int i = t / GTAB_ENTRIES, b = t % GTAB_ENTRIES;
+    jac_pt base = bases[i];
+    jac_pt acc = jac_identity();
+    for (int bit = 7; bit >= 0; bit--) {
+        acc = jac_dbl(acc);
+        if ((b >> bit) & 1) acc = jac_add(acc, base);
+    }
+    fp6 x, y;
+    bool inf;
+    jac_to_affine(acc, x, y, inf);
+    uint64_t* o = gtab + (size_t)t * 12;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        o[k] = x.c[k];
+        o[6 + k] = y.c[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: integer-multiply roofline calibration.  8 independent accumulator chains per thread of
+// 32x32+64 -> 64 multiply-adds (IMAD.WIDE.U32), no memory traffic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_imad_peak(int iters, uint64_t* sink) {
+    uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 977u;
+    uint64_t acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+        }
+        b += (uint32_t)acc[0];
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= acc[k];
+    if (s == 0x123456789abcdefULL) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static int alloc_soa(schnorr_b200_ctx* ctx, size_t n, soa_batch* b) {
+    void *p, *f, *sf;
+    if (int rc = ensure_scratch(ctx, SL_A, sizeof(ulonglong2) * SOA_PLANES * n, &p)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_B, n, &f)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_C, n, &sf)) return rc;
+    b->planes = (ulonglong2*)p;
+    b->flags = (uint8_t*)f;
+    b->sig_flag = (uint8_t*)sf;
+    b->n = n;
+    return 0;
+}
+
+// host -> device staging helper
+static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t bytes, void** dev) {
+    if (int rc = ensure_scratch(ctx, slot, bytes, dev)) return rc;
+    if (host && bytes) CUDA_TRY(ctx, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+#include "batch.cuh"
+
+extern "C" {
+
+int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
+    if (!out) return SCHNORR_B200_EARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        (void)cudaGetLastError();
+        return SCHNORR_B200_ENODEV;
+    }
+    schnorr_b200_ctx* ctx = new schnorr_b200_ctx();
+    ctx->device = device;
+    auto fail = [&](int rc) {
+        fprintf(stderr, "schnorr_b200_create: %s\n", ctx->err.c_str());
+        schnorr_b200_destroy(ctx);
+        return rc;
+    };
+#define CREATE_TRY(expr)                                                          \
+    do {                                                                          \
+        cudaError_t e_ = (expr);                                                  \
+        if (e_ != cudaSuccess) {                                                  \
+            ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e_);        \
+            return fail(SCHNORR_B200_ECUDA);                                      \
+        }                                                                         \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CREATE_TRY(cudaEventCreate(&ctx->ev_k0));
+    CREATE_TRY(cudaEventCreate(&ctx->ev_k1));
+    CREATE_TRY(cudaMemcpyToSymbol(c_ark, RESCUE_ARK, sizeof(uint64_t) * 2 * RESCUE_ROUNDS * 12));
+    CREATE_TRY(cudaMemcpyToSymbol(c_q_wnaf5, CHEETAH_Q_WNAF5, 256));
+    CREATE_TRY(cudaMalloc(&ctx->gtab, GTAB_U64 * sizeof(uint64_t)));
+    jac_pt* bases = nullptr;
+    CREATE_TRY(cudaMalloc(&bases, sizeof(jac_pt) * GTAB_WINDOWS));
+    fp6 gx, gy;
+    memcpy(gx.c, CHEETAH_GX, 48);
+    memcpy(gy.c, CHEETAH_GY, 48);
+    k_gtab_bases<<<1, GTAB_WINDOWS, 0, ctx->stream>>>(bases, gx, gy);
+    k_gtab_fill<<<GTAB_WINDOWS * GTAB_ENTRIES / 128, 128, 0, ctx->stream>>>(bases, ctx->gtab);
+    ctx->launches += 2;
+    CREATE_TRY(cudaGetLastError());
+    CREATE_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(bases);
+#undef CREATE_TRY
+    *out = ctx;
+    return SCHNORR_B200_OK;
+}
+
+void schnorr_b200_destroy(schnorr_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (int s = 0; s < SL_COUNT; s++)
+        if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
+    if (ctx->gtab) cudaFree(ctx->gtab);
+    if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* schnorr_b200_last_error(const schnorr_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int schnorr_b200_set_stream(schnorr_b200_ctx* ctx, void* stream) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_synchronize(schnorr_b200_ctx* ctx) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int schnorr_b200_last_kernel_ms(schnorr_b200_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_k1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+    return SCHNORR_B200_OK;
+}
+
+// ---- hash_messages ---------------------------------------------------------------------------
+int schnorr_b200_hash_messages_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* rx48, const uint8_t* pk96,
+                                   const uint8_t* msgs, const uint64_t* msg_off, uint8_t* digests) {
+    if (!ctx || (n && (!rx48 || !pk96 || !msg_off || !digests))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    k_hash<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, ctx->stream>>>(n, rx48, pk96, msgs, msg_off, digests);
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+int schnorr_b200_hash_messages(schnorr_b200_ctx* ctx, size_t n, const uint8_t* rx48, const uint8_t* pk96,
+                               const uint8_t* msgs, const uint64_t* msg_off, uint8_t* digests) {
+    if (!ctx || (n && (!rx48 || !pk96 || !msg_off || !digests))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    void *d_rx, *d_pk, *d_m, *d_off, *d_out;
+    if (int rc = stage_in(ctx, SL_D, rx48, n * 48, &d_rx)) return rc;
+    if (int rc = stage_in(ctx, SL_E, pk96, n * 96, &d_pk)) return rc;
+    if (int rc = stage_in(ctx, SL_F, msgs, mb, &d_m)) return rc;
+    if (int rc = stage_in(ctx, SL_G, msg_off, (n + 1) * 8, &d_off)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n * 32, &d_out)) return rc;
+    if (int rc = schnorr_b200_hash_messages_dev(ctx, n, (uint8_t*)d_rx, (uint8_t*)d_pk, (uint8_t*)d_m, (uint64_t*)d_off,
+                                                (uint8_t*)d_out))
+        return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(digests, d_out, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- verify_many -----------------------------------------------------------------------------
+int schnorr_b200_verify_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                                 const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                                 uint8_t* verdicts) {
+    if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    soa_batch soa;
+    if (int rc = alloc_soa(ctx, n, &soa)) return rc;
+    k_ingest<<<grid_for(n, INGEST_THREADS), INGEST_THREADS, 0, ctx->stream>>>(n, sigs81, pk96, pk_inf, soa);
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    k_verify<<<grid_for(n, VERIFY_THREADS), VERIFY_THREADS, 0, ctx->stream>>>(soa, msgs, msg_off, ctx->gtab, verdicts);
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                             const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
+    if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_out;
+    if (int rc = stage_in(ctx, SL_D, sigs81, n * 81, &d_sig)) return rc;
+    if (int rc = stage_in(ctx, SL_E, pk96, n * 96, &d_pk)) return rc;
+    if (int rc = stage_in(ctx, SL_F, msgs, mb, &d_m)) return rc;
+    if (int rc = stage_in(ctx, SL_G, msg_off, (n + 1) * 8, &d_off)) return rc;
+    if (pk_inf)
+        if (int rc = stage_in(ctx, SL_I, pk_inf, n, &d_inf)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n, &d_out)) return rc;
+    if (int rc = schnorr_b200_verify_many_dev(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
+                                              (uint64_t*)d_off, (uint8_t*)d_out))
+        return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- keygen / sign ---------------------------------------------------------------------------
+int schnorr_b200_keygen_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, uint8_t* pk96, uint8_t* pk_inf) {
+    if (!ctx || (n && (!sk32 || !pk96))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    k_keygen<<<grid_for(n, SIGN_THREADS), SIGN_THREADS, 0, ctx->stream>>>(n, sk32, ctx->gtab, pk96, pk_inf);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_keygen(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, uint8_t* pk96, uint8_t* pk_inf) {
+    if (!ctx || (n && (!sk32 || !pk96))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_sk, *d_pk, *d_inf;
+    if (int rc = stage_in(ctx, SL_D, sk32, n * 32, &d_sk)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 96, &d_pk)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_I, n, &d_inf)) return rc;
+    if (int rc = schnorr_b200_keygen_dev(ctx, n, (uint8_t*)d_sk, (uint8_t*)d_pk, (uint8_t*)d_inf)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(pk96, d_pk, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(pk_inf, d_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_sign_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, const uint8_t* pk96,
+                               const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                               const uint8_t* nonce32, uint8_t* sigs81) {
+    if (!ctx || (n && (!sk32 || !pk96 || !msg_off || !nonce32 || !sigs81))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    k_sign<<<grid_for(n, SIGN_THREADS), SIGN_THREADS, 0, ctx->stream>>>(n, sk32, pk96, pk_inf, msgs, msg_off, nonce32,
+                                                                        ctx->gtab, sigs81);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, const uint8_t* pk96,
+                           const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* nonce32,
+                           uint8_t* sigs81) {
+    if (!ctx || (n && (!sk32 || !pk96 || !msg_off || !nonce32 || !sigs81))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    void *d_sk, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_nonce, *d_out;
+    if (int rc = stage_in(ctx, SL_D, sk32, n * 32, &d_sk)) return rc;
+    if (int rc = stage_in(ctx, SL_E, pk96, n * 96, &d_pk)) return rc;
+    if (int rc = stage_in(ctx, SL_F, msgs, mb, &d_m)) return rc;
+    if (int rc = stage_in(ctx, SL_G, msg_off, (n + 1) * 8, &d_off)) return rc;
+    if (pk_inf)
+        if (int rc = stage_in(ctx, SL_I, pk_inf, n, &d_inf)) return rc;
+    if (int rc = stage_in(ctx, SL_J, nonce32, n * 32, &d_nonce)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n * 81, &d_out)) return rc;
+    if (int rc = schnorr_b200_sign_many_dev(ctx, n, (uint8_t*)d_sk, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
+                                            (uint64_t*)d_off, (uint8_t*)d_nonce, (uint8_t*)d_out))
+        return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(sigs81, d_out, n * 81, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- codecs ----------------------------------------------------------------------------------
+int schnorr_b200_decompress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* in49, uint8_t* pk96, uint8_t* pk_inf,
+                            uint8_t* ok) {
+    if (!ctx || (n && (!in49 || !pk96 || !pk_inf || !ok))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_in, *d_pk, *d_inf, *d_ok;
+    if (int rc = stage_in(ctx, SL_D, in49, n * 49, &d_in)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 96, &d_pk)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_I, n, &d_inf)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n, &d_ok)) return rc;
+    k_decompress<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint8_t*)d_in, (uint8_t*)d_pk, (uint8_t*)d_inf,
+                                                            (uint8_t*)d_ok);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(pk96, d_pk, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pk_inf, d_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_compress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* pk96, const uint8_t* pk_inf, uint8_t* out49) {
+    if (!ctx || (n && (!pk96 || !out49))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_pk, *d_inf = nullptr, *d_out;
+    if (int rc = stage_in(ctx, SL_E, pk96, n * 96, &d_pk)) return rc;
+    if (pk_inf)
+        if (int rc = stage_in(ctx, SL_I, pk_inf, n, &d_inf)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n * 49, &d_out)) return rc;
+    k_compress<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_out);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out49, d_out, n * 49, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- roofline calibration --------------------------------------------------------------------
+int schnorr_b200_imad_peak(schnorr_b200_ctx* ctx, int iters, double* wide_mul_per_s, double* elapsed_ms) {
+    if (!ctx || iters <= 0 || !wide_mul_per_s) return SCHNORR_B200_EARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* sink;
+    if (int rc = ensure_scratch(ctx, SL_H, 64, &sink)) return rc;
+    int blocks = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    CUDA_TRY(ctx, cudaEventCreate(&a));
+    CUDA_TRY(ctx, cudaEventCreate(&b));
+    k_imad_peak<<<blocks, 256, 0, ctx->stream>>>(iters / 8 + 1, (uint64_t*)sink);  // warm-up
+    CUDA_TRY(ctx, cudaEventRecord(a, ctx->stream));
+    k_imad_peak<<<blocks, 256, 0, ctx->stream>>>(iters, (uint64_t*)sink);
+    CUDA_TRY(ctx, cudaEventRecord(b, ctx->stream));
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    double total = (double)blocks * 256.0 * (double)iters * 8.0;
+    *wide_mul_per_s = total / (ms * 1e-3);
+    if (elapsed_ms) *elapsed_ms = ms;
+    return SCHNORR_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Per-signature building blocks of the verification path, written once and instantiated by the
+// CUDA kernels (schnorr_b200.cu) and, for CPU-side formula tests only, by tests/hostsim.
+//   Signature::verify            src/signature.rs:181-205
+//   KeyPair::sign                src/signature.rs:114-129   (device signer: synthetic inputs, §8 f1)
+//   PublicKey::from(&PrivateKey) src/public.rs:26-32
+#pragma once
+#include "curve.cuh"
+#include "rescue.cuh"
+
+namespace sb {
+
+enum verdict_t : uint8_t {
+    VERDICT_OK = 0,
+    VERDICT_INVALID_PUBLIC_KEY = 1,  // SignatureError::InvalidPublicKey  src/error.rs:15
+    VERDICT_INVALID_SIGNATURE = 2,   // SignatureError::InvalidSignature  src/error.rs:17
+    VERDICT_MALFORMED = 3,           // inputs on which the reference panics / that its types cannot hold
+};
+
+// Everything after the challenge hash: subgroup check, h*P + e*G, x-only comparison.
+// `x_ok` = sig.x limbs canonical (the reference unwraps Fp6::from_bytes AFTER the subgroup check,
+// src/signature.rs:182-186, so an off-subgroup key wins over a malformed x).
+SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
+                             const scalar& h, const uint64_t* __restrict__ gtab) {
+    jac_pt T[8];
+    build_odd_table(T, jac_from_affine(pk_x, pk_y, pk_inf));
+    if (!torsion_free_with_table(T)) return VERDICT_INVALID_PUBLIC_KEY;
+    if (!x_ok) return VERDICT_MALFORMED;
+    jac_pt r = double_base_mul(T, h, e, gtab);
+    return jac_x_equals(r, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
+}
+
+// Challenge: h = Scalar::from_bits_vartime(hash_message(R.x, P, m))  (src/signature.rs:188-192).
+// The identity public key hashes as x = y = 0 (its in-memory coordinates).
+SB_DEV scalar challenge_scalar(const fp6& sig_x, const fp6& pk_x, const fp6& pk_y, bool pk_inf, const uint8_t* msg,
+                               uint64_t len) {
+    fp6 px = pk_inf ? fp6_zero() : pk_x;
+    fp_t py0 = pk_inf ? 0 : pk_y.c[0];
+    fp_t d[4];
+    hash_message(sig_x, px, py0, msg, len, d);
+    return digest_to_scalar(d);
+}
+
+}  // namespace sb

@@ -1,0 +1,224 @@
+"""Array-level host API over the C ABI: one `Engine` = one `schnorr_b200_ctx` on one GPU.
+
+Buffers may be numpy arrays (host), torch tensors (host-pinned or CUDA) or raw integer addresses.
+The `*_dev` methods take device buffers, enqueue on the engine's stream and do not synchronise;
+the plain methods take host buffers and run the same kernels with the copies inside the call.
+Layouts are those of include/schnorr_b200.h (the reference's own byte encodings).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+OK, INVALID_PUBLIC_KEY, INVALID_SIGNATURE, MALFORMED = 0, 1, 2, 3
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("buffers must be C-contiguous")
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor
+        if not x.is_contiguous():
+            raise ValueError("buffers must be contiguous")
+        return C.c_void_p(x.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(x))
+
+
+def _u8(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if cols is not None and (a.ndim != 2 or a.shape[1] != cols):
+        raise ValueError("expected an [n,%d] uint8 array, got %r" % (cols, a.shape))
+    return a
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.schnorr_b200_create(int(device), C.byref(h))
+        if rc != 0 or not h.value:
+            raise EngineError("schnorr_b200_create(device=%d) failed with %d: a CUDA device is required "
+                              "(there is no CPU fallback)" % (device, rc))
+        self._h = h
+        self.device = int(device)
+
+    # ---- lifecycle -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.schnorr_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._L.schnorr_b200_last_error(self._h)
+            raise EngineError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._L.schnorr_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)), "set_stream")
+
+    def synchronize(self):
+        self._check(self._L.schnorr_b200_synchronize(self._h), "synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.schnorr_b200_launch_count(self._h))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(self._L.schnorr_b200_last_kernel_ms(self._h, C.byref(ms)), "last_kernel_ms")
+        return float(ms.value)
+
+    # ---- host-buffer entry points --------------------------------------------------------
+    def hash_messages(self, rx48, pk96, msgs, off):
+        rx48, pk96, msgs = _u8(rx48, 48), _u8(pk96, 96), _u8(msgs)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = rx48.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        out = np.zeros((n, 32), dtype=np.uint8)
+        self._check(self._L.schnorr_b200_hash_messages(self._h, n, _ptr(rx48), _ptr(pk96), _ptr(msgs), _ptr(off),
+                                                       _ptr(out)), "hash_messages")
+        return out
+
+    @staticmethod
+    def _check_offsets(n, npk, off, msgs):
+        # the reference asserts equal lengths (src/batch.rs:37-44)
+        if npk != n:
+            raise AssertionError("We should have the same number of signatures than public keys")
+        if off.shape[0] != n + 1:
+            raise AssertionError("We should have the same number of messages than public keys")
+        if n and (int(off[-1]) > msgs.size or np.any(off[1:] < off[:-1])):
+            raise ValueError("message offsets out of range")
+
+    def verify_many(self, sigs81, pk96, pk_inf, msgs, off):
+        sigs81, pk96, msgs = _u8(sigs81, 81), _u8(pk96, 96), _u8(msgs)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = sigs81.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        inf = None if pk_inf is None else _u8(pk_inf)
+        out = np.full(n, 255, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_verify_many(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(inf), _ptr(msgs),
+                                                     _ptr(off), _ptr(out)), "verify_many")
+        return out
+
+    def verify_batch(self, sigs81, pk96, pk_inf, msgs, off, rand32):
+        """-> (verdict, lhs97, rhs97)"""
+        sigs81, pk96, msgs, rand32 = _u8(sigs81, 81), _u8(pk96, 96), _u8(msgs), _u8(rand32, 32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = sigs81.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        if rand32.shape[0] != n:
+            raise AssertionError("one randomiser per signature")
+        inf = None if pk_inf is None else _u8(pk_inf)
+        verdict = C.c_int(-1)
+        lhs = np.zeros(97, dtype=np.uint8)
+        rhs = np.zeros(97, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_verify_batch(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(inf), _ptr(msgs),
+                                                      _ptr(off), _ptr(rand32), C.byref(verdict), _ptr(lhs), _ptr(rhs)),
+                    "verify_batch")
+        return verdict.value, lhs, rhs
+
+    def batch_finish(self, partials192):
+        partials192 = _u8(partials192, 192)
+        verdict = C.c_int(-1)
+        lhs = np.zeros(97, dtype=np.uint8)
+        rhs = np.zeros(97, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_batch_finish(self._h, partials192.shape[0], _ptr(partials192),
+                                                      C.byref(verdict), _ptr(lhs), _ptr(rhs)), "batch_finish")
+        return verdict.value, lhs, rhs
+
+    def keygen(self, sk32):
+        sk32 = _u8(sk32, 32)
+        n = sk32.shape[0]
+        pk = np.zeros((n, 96), dtype=np.uint8)
+        inf = np.zeros(n, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_keygen(self._h, n, _ptr(sk32), _ptr(pk), _ptr(inf)), "keygen")
+        return pk, inf
+
+    def sign_many(self, sk32, pk96, pk_inf, msgs, off, nonce32):
+        sk32, pk96, msgs, nonce32 = _u8(sk32, 32), _u8(pk96, 96), _u8(msgs), _u8(nonce32, 32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = sk32.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        inf = None if pk_inf is None else _u8(pk_inf)
+        out = np.zeros((n, 81), dtype=np.uint8)
+        self._check(self._L.schnorr_b200_sign_many(self._h, n, _ptr(sk32), _ptr(pk96), _ptr(inf), _ptr(msgs), _ptr(off),
+                                                   _ptr(nonce32), _ptr(out)), "sign_many")
+        return out
+
+    def decompress(self, in49):
+        in49 = _u8(in49, 49)
+        n = in49.shape[0]
+        pk = np.zeros((n, 96), dtype=np.uint8)
+        inf = np.zeros(n, dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_decompress(self._h, n, _ptr(in49), _ptr(pk), _ptr(inf), _ptr(ok)), "decompress")
+        return pk, inf, ok
+
+    def compress(self, pk96, pk_inf=None):
+        pk96 = _u8(pk96, 96)
+        n = pk96.shape[0]
+        inf = None if pk_inf is None else _u8(pk_inf)
+        out = np.zeros((n, 49), dtype=np.uint8)
+        self._check(self._L.schnorr_b200_compress(self._h, n, _ptr(pk96), _ptr(inf), _ptr(out)), "compress")
+        return out
+
+    def imad_peak(self, iters=1 << 16):
+        w = C.c_double(0)
+        ms = C.c_double(0)
+        self._check(self._L.schnorr_b200_imad_peak(self._h, int(iters), C.byref(w), C.byref(ms)), "imad_peak")
+        return w.value, ms.value
+
+    # ---- raw-pointer entry points (host-pinned or device buffers; no shape checks) -------------
+    def verify_many_raw(self, n, sigs81, pk96, pk_inf, msgs, off, verdicts):
+        """Host variant on raw buffers (e.g. pinned torch tensors): copies + kernels + copy back."""
+        self._check(self._L.schnorr_b200_verify_many(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(pk_inf), _ptr(msgs),
+                                                     _ptr(off), _ptr(verdicts)), "verify_many")
+
+    def verify_many_dev(self, n, sigs81, pk96, pk_inf, msgs, off, verdicts):
+        self._check(self._L.schnorr_b200_verify_many_dev(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(pk_inf), _ptr(msgs),
+                                                         _ptr(off), _ptr(verdicts)), "verify_many_dev")
+
+    def hash_messages_dev(self, n, rx48, pk96, msgs, off, digests):
+        self._check(self._L.schnorr_b200_hash_messages_dev(self._h, n, _ptr(rx48), _ptr(pk96), _ptr(msgs), _ptr(off),
+                                                           _ptr(digests)), "hash_messages_dev")
+
+    def keygen_dev(self, n, sk32, pk96, pk_inf):
+        self._check(self._L.schnorr_b200_keygen_dev(self._h, n, _ptr(sk32), _ptr(pk96), _ptr(pk_inf)), "keygen_dev")
+
+    def sign_many_dev(self, n, sk32, pk96, pk_inf, msgs, off, nonce32, sigs81):
+        self._check(self._L.schnorr_b200_sign_many_dev(self._h, n, _ptr(sk32), _ptr(pk96), _ptr(pk_inf), _ptr(msgs),
+                                                       _ptr(off), _ptr(nonce32), _ptr(sigs81)), "sign_many_dev")
+
+    def batch_partial_dev(self, n, sigs81, pk96, pk_inf, msgs, off, rand32, partial192):
+        self._check(self._L.schnorr_b200_batch_partial_dev(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(pk_inf),
+                                                           _ptr(msgs), _ptr(off), _ptr(rand32), _ptr(partial192)),
+                    "batch_partial_dev")
+
+    def batch_finish_dev(self, n_partials, partials192, result216):
+        self._check(self._L.schnorr_b200_batch_finish_dev(self._h, n_partials, _ptr(partials192), _ptr(result216)),
+                    "batch_finish_dev")
+
+
+_DEFAULT = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Engine(device)
+    return _DEFAULT[device]

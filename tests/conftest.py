@@ -1,0 +1,50 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    """ctypes handle on the TEST-ONLY host build of the device headers (tests/hostsim)."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "hostsim")
+    so = os.path.join(d, "libhostsim.so")
+    src = os.path.join(d, "hostsim.cpp")
+    csrc = os.path.join(ROOT, "schnorr-sig_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-o", so, src])
+    lib = ctypes.CDLL(so)
+    lib.hs_gtab.restype = ctypes.c_void_p
+    for name in ("hs_fp_mul", "hs_fp_sqr", "hs_fp_add", "hs_fp_sub", "hs_fp_inv", "hs_fp_mul_small",
+                 "hs_fp_reduce160", "hs_rescue_inv_sbox"):
+        getattr(lib, name).restype = ctypes.c_uint64
+    return lib

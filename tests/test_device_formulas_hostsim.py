@@ -1,0 +1,240 @@
+"""CPU checks of the DEVICE headers' formulas (schnorr-sig_b200/csrc/*.cuh compiled for the host by
+tests/hostsim, PTX replaced by portable C) against the oracle.  This is host-logic coverage: the real
+parity tests run the CUDA kernels through the C ABI (tests/test_gpu_*.py, -m gpu)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cref
+import pyref as o
+from util import KAT96, make_workload, pt_from96, pt_to96, rand_fp, rand_fp6, rand_scalars, int_le
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+EDGE = [0, 1, 2, 7, 2**32 - 1, 2**32, 2**32 + 1, 2**63, o.P - 1, o.P - 2, o.P - 2**32, (o.P - 1) // 2, (o.P + 1) // 2]
+
+
+def test_fp_ops(hostsim):
+    rng = np.random.default_rng(1)
+    vals = EDGE + [int(x) for x in rand_fp(rng, 200)]
+    for a in vals[:40]:
+        for b in vals[:40]:
+            assert hostsim.hs_fp_mul(C.c_uint64(a), C.c_uint64(b)) == a * b % o.P
+            assert hostsim.hs_fp_add(C.c_uint64(a), C.c_uint64(b)) == (a + b) % o.P
+            assert hostsim.hs_fp_sub(C.c_uint64(a), C.c_uint64(b)) == (a - b) % o.P
+    for a in vals:
+        assert hostsim.hs_fp_sqr(C.c_uint64(a)) == a * a % o.P
+        assert hostsim.hs_fp_mul_small(C.c_uint64(a), C.c_uint32(7)) == 7 * a % o.P
+        assert hostsim.hs_fp_mul_small(C.c_uint64(a), C.c_uint32(2**32 - 1)) == (2**32 - 1) * a % o.P
+        if a:
+            assert hostsim.hs_fp_inv(C.c_uint64(a)) == pow(a, o.P - 2, o.P)
+        r = C.c_uint64(0)
+        ok = hostsim.hs_fp_sqrt(C.c_uint64(a * a % o.P), C.byref(r))
+        assert ok and r.value in (a, (o.P - a) % o.P)
+        assert hostsim.hs_rescue_inv_sbox(C.c_uint64(a)) == pow(a, o.INV_ALPHA, o.P)
+    assert not hostsim.hs_fp_sqrt(C.c_uint64(7), C.byref(C.c_uint64(0)))       # 7 generates Fp^*
+
+
+def test_fp_reduce160_full_range(hostsim):
+    rng = np.random.default_rng(2)
+    for _ in range(2000):
+        w = [int(x) for x in rng.integers(0, 2**32, 4, dtype=np.uint64)] + [int(rng.integers(0, 512))]
+        x = sum(v << (32 * i) for i, v in enumerate(w))
+        assert hostsim.hs_fp_reduce160(*[C.c_uint32(v) for v in w]) == x % o.P
+    top = [2**32 - 1] * 4 + [511]
+    assert hostsim.hs_fp_reduce160(*[C.c_uint32(v) for v in top]) == sum(v << (32 * i) for i, v in enumerate(top)) % o.P
+
+
+def test_fp6_mul_sqr_inv_sqrt(hostsim):
+    rng = np.random.default_rng(3)
+    cases = [rand_fp6(rng) for _ in range(60)]
+    cases += [np.array([o.P - 1] * 6, dtype=np.uint64), np.zeros(6, dtype=np.uint64),
+              np.array([1, 0, 0, 0, 0, 0], dtype=np.uint64), np.array([0, 0, 0, 0, 0, o.P - 1], dtype=np.uint64),
+              np.array([5, 0, 9, 0, 11, 0], dtype=np.uint64), np.array([0, 3, 0, 0, 0, 0], dtype=np.uint64)]
+    r = np.zeros(6, dtype=np.uint64)
+    for i, a in enumerate(cases):
+        b = cases[(i * 7 + 3) % len(cases)]
+        ta, tb = tuple(int(x) for x in a), tuple(int(x) for x in b)
+        hostsim.hs_fp6_mul(p(a), p(b), p(r))
+        assert tuple(int(x) for x in r) == o.f6_mul(ta, tb)
+        hostsim.hs_fp6_sqr(p(a), p(r))
+        assert tuple(int(x) for x in r) == o.f6_sqr(ta)
+        if any(ta):
+            hostsim.hs_fp6_inv(p(a), p(r))
+            assert tuple(int(x) for x in r) == o.f6_inv(ta)
+        sq = np.array(o.f6_sqr(ta), dtype=np.uint64)
+        ok = hostsim.hs_fp6_sqrt(p(sq), p(r))
+        assert ok and tuple(int(x) for x in r) in (ta, o.f6_neg(ta))
+        assert bool(hostsim.hs_fp6_lex_largest(p(a))) == o.f6_lex_largest(ta)
+    # non-squares are rejected (curve constant B) and agree with the oracle on random inputs
+    assert not hostsim.hs_fp6_sqrt(p(np.array(o.CURVE_B, dtype=np.uint64)), p(r))
+    for a in cases[:30]:
+        ok = hostsim.hs_fp6_sqrt(p(a), p(r))
+        assert bool(ok) == cref.fp6_sqrt(a)[0]
+
+
+def test_rescue_and_hash_message(hostsim):
+    rng = np.random.default_rng(4)
+    for _ in range(4):
+        s = rand_fp(rng, 12)
+        want = o.rescue_permutation([int(x) for x in s])
+        hostsim.hs_rescue_permutation(p(s))
+        assert [int(x) for x in s] == want
+    lens = [0, 1, 6, 7, 8, 13, 14, 15, 21, 49, 50, 80, 160, 163]
+    w = make_workload(5, len(lens), lens=lens)
+    want = cref.hash_messages(w["sigs"][:, :48], w["pk"], w["blob"], w["off"])
+    out = np.zeros(32, dtype=np.uint8)
+    for i, m in enumerate(w["msgs"]):
+        rx = np.frombuffer(bytes(w["sigs"][i, :48]), dtype=np.uint64).copy()
+        px = np.frombuffer(bytes(w["pk"][i, :48]), dtype=np.uint64).copy()
+        py0 = int(np.frombuffer(bytes(w["pk"][i, 48:56]), dtype=np.uint64)[0])
+        mb = np.frombuffer(m, dtype=np.uint8).copy() if m else np.zeros(1, dtype=np.uint8)
+        hostsim.hs_hash_message(p(rx), p(px), C.c_uint64(py0), p(mb), C.c_uint64(len(m)), p(out))
+        assert bytes(out) == bytes(want[i])
+
+
+def test_scalar_field(hostsim):
+    rng = np.random.default_rng(6)
+    r = np.zeros(32, dtype=np.uint8)
+    edge = [0, 1, o.Q - 1, o.Q - 2, 2**254, (o.Q - 1) // 2]
+    vals = edge + [int_le(s) for s in rand_scalars(rng, 30)]
+    for a in vals:
+        for b in vals[:12]:
+            A = np.frombuffer(a.to_bytes(32, "little"), dtype=np.uint8).copy()
+            B = np.frombuffer(b.to_bytes(32, "little"), dtype=np.uint8).copy()
+            hostsim.hs_sc_mul(p(A), p(B), p(r)); assert int_le(r) == a * b % o.Q
+            hostsim.hs_sc_add(p(A), p(B), p(r)); assert int_le(r) == (a + b) % o.Q
+            hostsim.hs_sc_sub(p(A), p(B), p(r)); assert int_le(r) == (a - b) % o.Q
+    for v in [0, o.Q - 1, o.Q, o.Q + 1, 2 * o.Q, 2 * o.Q + 5, 2**256 - 1] + [int_le(rng.integers(0, 256, 32, dtype=np.uint8)) for _ in range(20)]:
+        V = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8).copy()
+        hostsim.hs_sc_from_u256(p(V), p(r)); assert int_le(r) == v % o.Q
+        assert bool(hostsim.hs_sc_geq_q(p(V))) == (v >= o.Q)
+
+
+def test_regular_recoding(hostsim):
+    rng = np.random.default_rng(7)
+    d = np.zeros(64, dtype=np.int8)
+    for k in [1, 3, 15, 17, o.Q, o.Q - 2, 2**255 - 1] + [int_le(s) | 1 for s in rand_scalars(rng, 50)]:
+        K = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy()
+        hostsim.hs_recode_odd_w4(p(K), p(d))
+        assert all(int(x) % 2 != 0 and abs(int(x)) <= 15 for x in d)
+        assert sum(int(x) << (4 * i) for i, x in enumerate(d)) == k
+
+
+def test_point_formulas(hostsim):
+    rng = np.random.default_rng(8)
+    G = o.generator()
+    g96 = pt_to96(G)
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 4)] + [G, (o.KAT_X, o.KAT_Y)]
+    for a in pts:
+        for b in pts:
+            A, B = pt_to96(a), pt_to96(b)
+            want = o.pt_add(a, b)
+            hostsim.hs_pt_add(p(A), 0, p(B), 0, p(out), C.byref(oi))
+            assert (o.INF if oi.value else pt_from96(out)) == want
+            hostsim.hs_pt_madd(p(A), 0, p(B), 0, p(out), C.byref(oi))
+            assert (o.INF if oi.value else pt_from96(out)) == want
+        A = pt_to96(a)
+        hostsim.hs_pt_dbl(p(A), 0, p(out), C.byref(oi))
+        assert pt_from96(out) == o.pt_add(a, a)
+        # exceptional cases: P + (-P), identity operands
+        N = pt_to96(o.pt_neg(a))
+        hostsim.hs_pt_add(p(A), 0, p(N), 0, p(out), C.byref(oi)); assert oi.value == 1
+        hostsim.hs_pt_madd(p(A), 0, p(N), 0, p(out), C.byref(oi)); assert oi.value == 1
+        hostsim.hs_pt_add(p(A), 1, p(A), 0, p(out), C.byref(oi)); assert pt_from96(out) == a and not oi.value
+        hostsim.hs_pt_add(p(A), 0, p(A), 1, p(out), C.byref(oi)); assert pt_from96(out) == a and not oi.value
+        hostsim.hs_pt_madd(p(A), 1, p(A), 0, p(out), C.byref(oi)); assert pt_from96(out) == a and not oi.value
+        hostsim.hs_pt_madd(p(A), 0, p(A), 1, p(out), C.byref(oi)); assert pt_from96(out) == a and not oi.value
+    hostsim.hs_pt_dbl(p(g96), 1, p(out), C.byref(oi)); assert oi.value == 1
+    # a point of order 2 (y = 0) doubles to the identity: find one from the cofactor structure
+    kat = (o.KAT_X, o.KAT_Y)
+    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
+    assert t2 is not o.INF and t2[1] == o.F6_ZERO
+    T2 = pt_to96(t2)
+    hostsim.hs_pt_dbl(p(T2), 0, p(out), C.byref(oi)); assert oi.value == 1
+    hostsim.hs_pt_add(p(T2), 0, p(T2), 0, p(out), C.byref(oi)); assert oi.value == 1
+
+
+def test_torsion_check_including_small_order_points(hostsim):
+    kat = (o.KAT_X, o.KAT_Y)
+    assert hostsim.hs_torsion_free(p(pt_to96(o.generator())), 0) == 1
+    assert hostsim.hs_torsion_free(p(KAT96), 0) == 0
+    assert hostsim.hs_torsion_free(p(KAT96), 1) == 1            # identity
+    n = o.COFACTOR * o.Q
+    # points of small order 2, 5, 10, 29 and of order q*2: adversarial keys that hit P+P / P-P inside the chain
+    for f in (2, 5, 10, 29, 2 * 5 * 29 * 181):
+        pt = o.pt_mul(kat, n // f)
+        if pt is o.INF:
+            continue
+        assert hostsim.hs_torsion_free(p(pt_to96(pt)), 0) == int(o.is_torsion_free(pt)) == 0
+    mixed = o.pt_add(o.generator(), o.pt_mul(kat, n // 2))       # order 2q
+    assert hostsim.hs_torsion_free(p(pt_to96(mixed)), 0) == 0
+    rng = np.random.default_rng(9)
+    for s in rand_scalars(rng, 3):
+        pt = o.pt_mul(o.generator(), int_le(s))
+        assert hostsim.hs_torsion_free(p(pt_to96(pt)), 0) == 1
+
+
+def test_fixed_and_double_base(hostsim):
+    rng = np.random.default_rng(10)
+    G = o.generator()
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+    ks = [0, 1, 255, 256, o.Q - 1, 2**248] + [int_le(s) for s in rand_scalars(rng, 4)]
+    for k in ks:
+        K = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy()
+        hostsim.hs_fixed_base_mul(p(K), p(out), C.byref(oi))
+        assert (o.INF if oi.value else pt_from96(out)) == o.pt_mul(G, k % o.Q)
+    P = o.pt_mul(G, 0x1234567)
+    P96 = pt_to96(P)
+    hs = [0, 1, 2, 3, o.Q - 1, o.Q - 2] + [int_le(s) for s in rand_scalars(rng, 4)]
+    for h in hs:
+        for e in (0, 5, int_le(rand_scalars(rng, 1)[0])):
+            H = np.frombuffer(h.to_bytes(32, "little"), dtype=np.uint8).copy()
+            E = np.frombuffer(e.to_bytes(32, "little"), dtype=np.uint8).copy()
+            hostsim.hs_double_base(p(P96), 0, p(H), p(E), p(out), C.byref(oi))
+            assert (o.INF if oi.value else pt_from96(out)) == o.pt_mul2(P, h, G, e)
+    # identity public key: result is e*G
+    E = np.frombuffer((77).to_bytes(32, "little"), dtype=np.uint8).copy()
+    hostsim.hs_double_base(p(P96), 1, p(E), p(E), p(out), C.byref(oi))
+    assert pt_from96(out) == o.pt_mul(G, 77)
+
+
+def test_decompress(hostsim):
+    w = make_workload(12, 6)
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+    for i in range(6):
+        rec = w["sigs"][i, :49].copy()
+        ok, want, winf = cref.decompress(rec)
+        assert hostsim.hs_decompress(p(rec), p(out), C.byref(oi)) == 1 and ok
+        assert bytes(out) == bytes(want)
+        rec[48] ^= 0x40
+        assert hostsim.hs_decompress(p(rec), p(out), C.byref(oi)) == 1
+        assert bytes(out[:48]) == bytes(want[:48]) and bytes(out[48:]) != bytes(want[48:])
+    for bad in (np.zeros(49, np.uint8), np.full(49, 255, np.uint8)):
+        assert hostsim.hs_decompress(p(bad), p(out), C.byref(oi)) == 0
+    ident = np.zeros(49, np.uint8); ident[48] = 0x80
+    assert hostsim.hs_decompress(p(ident), p(out), C.byref(oi)) == 1 and oi.value == 1
+
+
+def test_verify_one_matches_oracle_verdicts(hostsim):
+    lens = [8, 0, 7, 80, 160, 3]
+    w = make_workload(13, len(lens), lens=lens)
+    sigs, pk = w["sigs"].copy(), w["pk"].copy()
+    sigs[1, 49:] = 0                      # e := 0
+    pk[2] = KAT96                         # off-subgroup key
+    sigs[3, :48] = 0; sigs[3, 48] = 0x80  # x := identity encoding
+    sigs[4, 8:16] = 0xFF                  # non-canonical limb
+    want = cref.verify_many(sigs, pk, w["inf"], w["blob"], w["off"])
+    assert list(want) == [0, 2, 1, 2, 3, 0]
+    for i, m in enumerate(w["msgs"]):
+        mb = np.frombuffer(m, dtype=np.uint8).copy() if m else np.zeros(1, dtype=np.uint8)
+        got = hostsim.hs_verify_one(p(sigs[i].copy()), p(pk[i].copy()), 0, p(mb), C.c_uint64(len(m)))
+        assert got == want[i]
