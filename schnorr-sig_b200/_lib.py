@@ -46,7 +46,7 @@ def lib():
     """Loads (building first if stale) schnorr-sig_b200/csrc/libschnorr_b200.so."""
     global _LIB
     if _LIB is None:
-        so = _build.build()
+        so = os.environ.get("SCHNORR_B200_LIB") or _build.build()   # override = kernel-variant experiments only
         if not os.path.exists(so):
             raise RuntimeError("libschnorr_b200.so is missing and could not be built; there is no CPU fallback")
         L = C.CDLL(so)

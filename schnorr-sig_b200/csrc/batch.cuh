@@ -368,7 +368,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
                                                                          (uint32_t*)d_sorted, buckets);
     cudaEventRecord(ctx->ev_k1, st);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, 64), 64, 0, st>>>(pl, buckets, chunk_out);
-    k_msm_window_fold<<<1, 32, 0, st>>>(pl, chunk_out, windows);
+    k_msm_window_fold<<<grid_for((size_t)pl.K, 32), 32, 0, st>>>(pl, chunk_out, windows);
     k_msm_horner<<<1, 1, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
     ctx->launches += 11;
     CUDA_TRY(ctx, cudaGetLastError());

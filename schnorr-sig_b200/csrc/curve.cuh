@@ -5,9 +5,14 @@
 // result is compared through its affine x only (src/signature.rs:200), so any algorithm producing
 // the same group element is bit-exact after normalisation.
 //
-// All formulas are branch-free on the common path; the exceptional inputs (identity operands,
-// P + P, P + (-P)) are handled exactly, because adversarial public keys of small order DO reach
-// them (the reference's own test uses an off-subgroup key, src/signature.rs:385-406).
+// The exceptional inputs (identity operands, P + P, P + (-P)) are handled exactly, on rarely taken
+// branches, because adversarial public keys of small order DO reach them (the reference's own test
+// uses an off-subgroup key, src/signature.rs:385-406).
+//
+// Code-size discipline: the hot loops call ONE out-of-line copy each of jac_dbl_mem / jac_add_mem /
+// jac_madd_mem (operating on points held in thread-local memory), which in turn call one copy of
+// fp6_mul / fp6_sqr.  The whole scalar-multiplication loop then fits the instruction cache and the
+// accumulator does not pin 36 registers across calls.
 #pragma once
 #include "fp6.cuh"
 #include "scalar.cuh"
@@ -16,9 +21,6 @@ namespace sb {
 
 struct jac_pt {
     fp6 X, Y, Z;
-};
-struct aff_pt {
-    fp6 x, y;  // identity is carried out of band (table entries are never the identity)
 };
 
 SB_DEV jac_pt jac_identity() { return jac_pt{fp6_one(), fp6_one(), fp6_zero()}; }
@@ -29,9 +31,6 @@ SB_DEV jac_pt jac_from_affine(const fp6& x, const fp6& y, bool inf) {
     return r;
 }
 SB_DEV jac_pt jac_neg(const jac_pt& p) { return jac_pt{p.X, fp6_neg(p.Y), p.Z}; }
-SB_DEV jac_pt jac_select(bool pick_b, const jac_pt& a, const jac_pt& b) {
-    return jac_pt{fp6_select(pick_b, a.X, b.X), fp6_select(pick_b, a.Y, b.Y), fp6_select(pick_b, a.Z, b.Z)};
-}
 
 // dbl-2007-bl with a = 1: 1M + 8S.  Complete: Z = 0 or Y = 0 (order-2 point) both give Z3 = 0.
 SB_DEV jac_pt jac_dbl(const jac_pt& p) {
@@ -50,8 +49,10 @@ SB_DEV jac_pt jac_dbl(const jac_pt& p) {
     return r;
 }
 
-// add-2007-bl: 11M + 5S, with exact handling of identity operands and of P1 == +-P2.
+// add-2007-bl: 11M + 5S.  q_neg adds -q.
 SB_DEV jac_pt jac_add(const jac_pt& p, const jac_pt& q) {
+    bool p_inf = fp6_is_zero(p.Z), q_inf = fp6_is_zero(q.Z);
+    if (p_inf | q_inf) return p_inf ? q : p;  // rare
     fp6 Z1Z1 = fp6_sqr(p.Z);
     fp6 Z2Z2 = fp6_sqr(q.Z);
     fp6 U1 = fp6_mul(p.X, Z2Z2);
@@ -60,8 +61,10 @@ SB_DEV jac_pt jac_add(const jac_pt& p, const jac_pt& q) {
     fp6 S2 = fp6_mul(fp6_mul(q.Y, p.Z), Z1Z1);
     fp6 H = fp6_sub(U2, U1);
     fp6 rr = fp6_sub(S2, S1);
-    bool p_inf = fp6_is_zero(p.Z), q_inf = fp6_is_zero(q.Z);
-    if (!p_inf && !q_inf && fp6_is_zero(H) && fp6_is_zero(rr)) return jac_dbl(p);  // rare: P1 == P2
+    if (fp6_is_zero(H)) {  // rare: same x
+        if (fp6_is_zero(rr)) return jac_dbl(p);
+        return jac_identity();
+    }
     fp6 I = fp6_sqr(fp6_dbl(H));
     fp6 J = fp6_mul(H, I);
     fp6 r2 = fp6_dbl(rr);
@@ -69,21 +72,23 @@ SB_DEV jac_pt jac_add(const jac_pt& p, const jac_pt& q) {
     jac_pt r;
     r.X = fp6_sub(fp6_sub(fp6_sqr(r2), J), fp6_dbl(V));
     r.Y = fp6_sub(fp6_mul(r2, fp6_sub(V, r.X)), fp6_dbl(fp6_mul(S1, J)));
-    r.Z = fp6_mul(fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);  // H = 0, rr != 0 -> identity
-    r = jac_select(q_inf, r, p);
-    r = jac_select(p_inf, r, q);
+    r.Z = fp6_mul(fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
     return r;
 }
 
-// madd-2007-bl (q affine, never the identity unless q_inf): 7M + 4S
+// madd-2007-bl (q affine): 7M + 4S
 SB_DEV jac_pt jac_madd(const jac_pt& p, const fp6& qx, const fp6& qy, bool q_inf) {
+    if (q_inf) return p;
+    if (fp6_is_zero(p.Z)) return jac_pt{qx, qy, fp6_one()};
     fp6 Z1Z1 = fp6_sqr(p.Z);
     fp6 U2 = fp6_mul(qx, Z1Z1);
     fp6 S2 = fp6_mul(fp6_mul(qy, p.Z), Z1Z1);
     fp6 H = fp6_sub(U2, p.X);
     fp6 rr = fp6_sub(S2, p.Y);
-    bool p_inf = fp6_is_zero(p.Z);
-    if (!p_inf && !q_inf && fp6_is_zero(H) && fp6_is_zero(rr)) return jac_dbl(p);  // rare: P1 == P2
+    if (fp6_is_zero(H)) {  // rare: same x
+        if (fp6_is_zero(rr)) return jac_dbl(p);
+        return jac_identity();
+    }
     fp6 HH = fp6_sqr(H);
     fp6 I = fp6_dbl(fp6_dbl(HH));
     fp6 J = fp6_mul(H, I);
@@ -93,33 +98,46 @@ SB_DEV jac_pt jac_madd(const jac_pt& p, const fp6& qx, const fp6& qy, bool q_inf
     r.X = fp6_sub(fp6_sub(fp6_sqr(r2), J), fp6_dbl(V));
     r.Y = fp6_sub(fp6_mul(r2, fp6_sub(V, r.X)), fp6_dbl(fp6_mul(p.Y, J)));
     r.Z = fp6_sub(fp6_sub(fp6_sqr(fp6_add(p.Z, H)), Z1Z1), HH);
-    r = jac_select(q_inf, r, p);
-    r = jac_select(p_inf, r, jac_from_affine(qx, qy, q_inf));
     return r;
 }
 
-// affine x of a Jacobian point; the identity reads as x = 0
-SB_DEV fp6 jac_affine_x(const jac_pt& p) {
-    fp6 zi = fp6_inv(p.Z);  // 0 for the identity
-    return fp6_mul(p.X, fp6_sqr(zi));
+// ---- out-of-line, in-memory forms used by every loop -------------------------------------------
+SB_DEV_NOINLINE void jac_dbl_mem(jac_pt* p) { *p = jac_dbl(*p); }
+SB_DEV_NOINLINE void jac_add_mem(jac_pt* acc, const jac_pt* q, bool q_neg) {
+    jac_pt t = *q;
+    if (q_neg) t.Y = fp6_neg(t.Y);
+    *acc = jac_add(*acc, t);
 }
+// affine operand read from a table of 12 x u64 entries (x || y)
+SB_DEV_NOINLINE void jac_madd_mem(jac_pt* acc, const uint64_t* __restrict__ ent, bool q_neg, bool q_skip) {
+    fp6 qx, qy;
+#if defined(__CUDA_ARCH__)
+    const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(ent);
+    ulonglong2 a = e2[0], b = e2[1], c = e2[2], d = e2[3], e = e2[4], f = e2[5];
+    qx = fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
+    qy = fp6{{d.x, d.y, e.x, e.y, f.x, f.y}};
+#else
+    for (int k = 0; k < 6; k++) {
+        qx.c[k] = ent[k];
+        qy.c[k] = ent[6 + k];
+    }
+#endif
+    if (q_neg) qy = fp6_neg(qy);
+    *acc = jac_madd(*acc, qx, qy, q_skip);
+}
+
 SB_DEV void jac_to_affine(const jac_pt& p, fp6& x, fp6& y, bool& inf) {
     inf = fp6_is_zero(p.Z);
-    fp6 zi = fp6_inv(p.Z);
+    fp6 zi = fp6_inv(p.Z);  // 0 for the identity -> x = y = 0
     fp6 zi2 = fp6_sqr(zi);
     x = fp6_mul(p.X, zi2);
     y = fp6_mul(p.Y, fp6_mul(zi2, zi));
 }
-// X == x * Z^2 without an inversion (final comparison of verify); identity compares equal to x = 0 only
+// X == x * Z^2 without an inversion (final comparison of verify); the identity reads as x = 0
+// (SURVEY.md §8 a9), so it compares equal to x = 0 only.
 SB_DEV bool jac_x_equals(const jac_pt& p, const fp6& x) {
     if (fp6_is_zero(p.Z)) return fp6_is_zero(x);
     return fp6_eq(p.X, fp6_mul(x, fp6_sqr(p.Z)));
-}
-SB_DEV bool aff_on_curve(const fp6& x, const fp6& y) {
-    fp6 rhs = fp6_add(fp6_mul(fp6_sqr(x), x), x);
-    rhs.c[0] = fp_add(rhs.c[0], 395);
-    rhs.c[1] = fp_add(rhs.c[1], 1);
-    return fp6_eq(fp6_sqr(y), rhs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,10 +145,14 @@ SB_DEV bool aff_on_curve(const fp6& x, const fp6& y) {
 // Shared by the subgroup check (width-5 NAF of the constant q) and by the regular signed-odd
 // window-4 recoding of the challenge scalar.
 SB_DEV void build_odd_table(jac_pt* T, const jac_pt& P) {
-    jac_pt P2 = jac_dbl(P);
+    jac_pt P2 = P;
+    jac_dbl_mem(&P2);
     T[0] = P;
 #pragma unroll 1
-    for (int k = 1; k < 8; k++) T[k] = jac_add(T[k - 1], P2);
+    for (int k = 1; k < 8; k++) {
+        T[k] = T[k - 1];
+        jac_add_mem(&T[k], &P2, false);
+    }
 }
 
 #if defined(__CUDACC__)
@@ -149,32 +171,25 @@ SB_DEV bool torsion_free_with_table(const jac_pt* T) {
     jac_pt acc = T[d >> 1];
 #pragma unroll 1
     for (int i = top - 1; i >= 0; i--) {
-        acc = jac_dbl(acc);
+        jac_dbl_mem(&acc);
         int di = SB_QWNAF(i);
         if (di != 0) {  // warp-uniform branch
             int idx = (di < 0 ? -di : di) >> 1;
-            jac_pt t = T[idx];
-            if (di < 0) t.Y = fp6_neg(t.Y);
-            acc = jac_add(acc, t);
+            jac_add_mem(&acc, &T[idx], di < 0);
         }
     }
     return jac_is_identity(acc);
 }
 
 // Regular signed-odd recoding, window 4 (Joye-Tunstall): an ODD k < 2^255 becomes 64 odd digits
-// d_i in {+-1, +-3, ..., +-15} with k = sum d_i 16^i.  Digits are returned packed: bit 4 = sign,
-// bits 0..2 = table index (|d|-1)/2.
+// d_i in {+-1, +-3, ..., +-15} with k = sum d_i 16^i:  d_i = (k mod 32) - 16, k <- (k - d_i) / 16.
+// Digits are returned packed: bit 4 = sign, bits 0..2 = table index (|d|-1)/2.
 SB_DEV void recode_odd_w4(const scalar& k, uint8_t* digits /*64*/) {
-    // d_i = (k mod 32) - 16; k = (k - d_i) / 16  <=>  with odd k: d_i = ((k >> 4i) & 31 | 1) ... evaluated
-    // incrementally on the bit string: t_i = bits[4i .. 4i+4] of the running value.
-    // Closed form for odd k: d_i = 2 * b_{i}' - 15 ... ; we use the simple carry-free identity
-    //   d_i = (w_i | 1) - 16 * (1 - c_i) ...  -> implemented as the textbook loop on a copy of k.
     scalar v = k;
 #pragma unroll 1
     for (int i = 0; i < 63; i++) {
-        int w = (int)(v.l[0] & 31);       // k mod 2^(w+1)
-        int d = w - 16;                   // odd, in [-15, 15]
-        // v = (v - d) >> 4 : v - d = v - w + 16; low 5 bits of v become 10000b then shift by 4
+        int d = (int)(v.l[0] & 31) - 16;  // odd, in [-15, 15]
+        // v - d has low five bits 10000b; dividing by 16 leaves an odd value again
         v.l[0] = (v.l[0] & ~31u) | 16u;
 #pragma unroll
         for (int j = 0; j < 7; j++) v.l[j] = (v.l[j] >> 4) | (v.l[j + 1] << 28);
@@ -182,78 +197,53 @@ SB_DEV void recode_odd_w4(const scalar& k, uint8_t* digits /*64*/) {
         int a = d < 0 ? -d : d;
         digits[i] = (uint8_t)(((d < 0) ? 16 : 0) | (a >> 1));
     }
-    int d = (int)(v.l[0] & 31);  // remaining value, odd, <= 15 for k < 2^255 + ...
-    digits[63] = (uint8_t)(d >> 1);
+    digits[63] = (uint8_t)((v.l[0] & 31) >> 1);  // remaining value: odd and <= 9 for k < 2^255
 }
 
-// h*P + e*G with the odd table of P and a byte-indexed fixed-base table of G:
-//   gtab[(i*256 + b)] = b * 256^i * G  (affine x||y as 12 u64; entry b = 0 unused).
-// h, e canonical scalars.  (multiply_double_with_basepoint_vartime, src/signature.rs:196-198.)
+static constexpr int GTAB_ENTRY_U64 = 12;
+// entry (window i, byte b) of the fixed-base table: b * 256^i * G as affine x || y
+SB_DEV const uint64_t* gtab_entry(const uint64_t* __restrict__ gtab, int i, uint32_t b) {
+    return gtab + ((size_t)(i * 256 + (b ? b : 1))) * GTAB_ENTRY_U64;
+}
+
+// acc += k * G using the byte-indexed table (32 mixed additions, no doublings)
+SB_DEV void fixed_base_accumulate(jac_pt* acc, const scalar& k, const uint64_t* __restrict__ gtab) {
+#pragma unroll 1
+    for (int i = 0; i < 32; i++) {
+        uint32_t b = (k.l[i >> 2] >> (8 * (i & 3))) & 0xff;
+        jac_madd_mem(acc, gtab_entry(gtab, i, b), false, b == 0);
+    }
+}
+
+// h*P + e*G with the odd table of P and the fixed-base table of G; h, e canonical scalars.
+// (multiply_double_with_basepoint_vartime, src/signature.rs:196-198.)
 SB_DEV jac_pt double_base_mul(const jac_pt* T, const scalar& h, const scalar& e, const uint64_t* __restrict__ gtab) {
-    // make the variable-base scalar odd: for even h use q - h (odd) and flip every digit's sign
+    // make the variable-base scalar odd: for even h use q - h (odd) and flip every digit's sign;
+    // h = 0 uses k = q itself ([q]P = O for a key that passed the subgroup check).
     bool flip = (h.l[0] & 1) == 0;
-    scalar k = flip ? sc_cond_sub_q(sc_neg(h)) : h;
-    if (sc_is_zero(h)) {  // q - 0 = q is not canonical; [q]P = O anyway: use k = q directly
+    scalar k = flip ? sc_neg(h) : h;
+    if (sc_is_zero(h)) {
 #pragma unroll
         for (int i = 0; i < 8; i++) k.l[i] = SB_CONST_Q(i);
     }
     uint8_t dg[64];
     recode_odd_w4(k, dg);
-    jac_pt acc = jac_identity();
+    jac_pt acc = T[dg[63] & 7];
+    if (((dg[63] >> 4) & 1) != (flip ? 1 : 0)) acc.Y = fp6_neg(acc.Y);
 #pragma unroll 1
-    for (int i = 63; i >= 0; i--) {
-        if (i != 63) {
+    for (int i = 62; i >= 0; i--) {
 #pragma unroll 1
-            for (int s = 0; s < 4; s++) acc = jac_dbl(acc);
-        }
-        jac_pt t = T[dg[i] & 7];
-        bool neg = ((dg[i] >> 4) & 1) != (flip ? 1 : 0);
-        if (neg) t.Y = fp6_neg(t.Y);
-        acc = jac_add(acc, t);
+        for (int s = 0; s < 4; s++) jac_dbl_mem(&acc);
+        jac_add_mem(&acc, &T[dg[i] & 7], ((dg[i] >> 4) & 1) != (flip ? 1 : 0));
     }
-    // fixed base: 32 byte-windows, no doublings
-#pragma unroll 1
-    for (int i = 0; i < 32; i++) {
-        uint32_t b = (e.l[i >> 2] >> (8 * (i & 3))) & 0xff;
-        const uint64_t* ent = gtab + ((size_t)(i * 256 + (b ? b : 1))) * 12;
-        fp6 gx, gy;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            gx.c[c] = ent[c];
-            gy.c[c] = ent[6 + c];
-        }
-        acc = jac_madd(acc, gx, gy, b == 0);
-    }
+    fixed_base_accumulate(&acc, e, gtab);
     return acc;
 }
 
-// k*G with the same byte table (BASEPOINT_TABLE * scalar: src/public.rs:29, src/signature.rs:67,116,
-// src/batch.rs:98-100)
+// k*G (BASEPOINT_TABLE * scalar: src/public.rs:29, src/signature.rs:67,116, src/batch.rs:98-100)
 SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab) {
     jac_pt acc = jac_identity();
-#pragma unroll 1
-    for (int i = 0; i < 32; i++) {
-        uint32_t b = (k.l[i >> 2] >> (8 * (i & 3))) & 0xff;
-        const uint64_t* ent = gtab + ((size_t)(i * 256 + (b ? b : 1))) * 12;
-        fp6 gx, gy;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            gx.c[c] = ent[c];
-            gy.c[c] = ent[6 + c];
-        }
-        acc = jac_madd(acc, gx, gy, b == 0);
-    }
-    return acc;
-}
-
-// plain double-and-add k*P for table construction (not a hot path)
-SB_DEV jac_pt jac_mul_bits(const jac_pt& P, const scalar& k) {
-    jac_pt acc = jac_identity();
-#pragma unroll 1
-    for (int i = 255; i >= 0; i--) {
-        acc = jac_dbl(acc);
-        if ((k.l[i >> 5] >> (i & 31)) & 1) acc = jac_add(acc, P);
-    }
+    fixed_base_accumulate(&acc, k, gtab);
     return acc;
 }
 

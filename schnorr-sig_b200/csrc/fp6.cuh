@@ -138,7 +138,8 @@ SB_DEV fp6 fp6_mul_small(const fp6& a, uint32_t k) {
 struct fp3 {
     fp_t c[3];
 };
-SB_DEV fp3 fp3_mul(const fp3& a, const fp3& b) {
+// out of line (by value, register ABI): the square-root / inversion code stays compact
+SB_DEV_NOINLINE fp3 fp3_mul(fp3 a, fp3 b) {
     fp3 r;
     fp_t b7_1 = fp_mul7(b.c[1]), b7_2 = fp_mul7(b.c[2]);
     wide_acc w;
@@ -193,7 +194,7 @@ SB_DEV fp6 fp6_join(const fp3& a0, const fp3& a1) { return fp6{{a0.c[0], a1.c[0]
 
 // a^-1 through the tower Fp6 = Fp3[u]/(u^2 - v):  (a0 + a1 u)^-1 = (a0 - a1 u) / (a0^2 - v a1^2).
 // Returns 0 for a = 0.
-SB_DEV fp6 fp6_inv(const fp6& a) {
+SB_DEV_NOINLINE fp6 fp6_inv(fp6 a) {
     fp3 a0, a1;
     fp6_split(a, a0, a1);
     fp3 d = fp3_sub(fp3_sqr(a0), fp3_mulv(fp3_sqr(a1)));
@@ -233,11 +234,9 @@ SB_DEV bool fp_is_square(fp_t a) {
     return fp_sqr_n(fp_pow_2_32_m1(a), 31) == 1;
 }
 // Tonelli-Shanks in Fp: p - 1 = 2^32 * (2^32 - 1).  Returns false if a is not a square.
-SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
-    if (a == 0) {
-        out = 0;
-        return true;
-    }
+static constexpr fp_t FP_NONE = ~0ULL;  // not a canonical element: "no square root"
+SB_DEV_NOINLINE fp_t fp_sqrt_or_none(fp_t a) {
+    if (a == 0) return 0;
     fp_t x = fp_sqr_n(a, 31);        // a^((t+1)/2), t = 2^32 - 1
     fp_t b = fp_pow_2_32_m1(a);      // a^t
     fp_t g = 0x185629dcda58878cULL;  // FP_ROOT_OF_UNITY_2_32 = 7^t (include/cheetah_params.h)
@@ -247,7 +246,7 @@ SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
         fp_t bb = b;
         while (bb != 1) {
             bb = fp_sqr(bb);
-            if (++m == r) return false;
+            if (++m == r) return FP_NONE;
         }
         fp_t gs = fp_sqr_n(g, r - m - 1);
         g = fp_sqr(gs);
@@ -255,11 +254,17 @@ SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
         b = fp_mul(b, g);
         r = m;
     }
-    out = x;
+    return x;
+}
+SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
+    fp_t r = fp_sqrt_or_none(a);
+    if (r == FP_NONE) return false;
+    out = r;
     return true;
 }
 
 SB_DEV fp3 fp3_sqr_n(fp3 a, int n) {
+#pragma unroll 1
     for (int i = 0; i < n; i++) a = fp3_sqr(a);
     return a;
 }
@@ -273,13 +278,10 @@ SB_DEV fp_t fp3_norm(const fp3& a) {
 SB_DEV bool fp3_is_square(const fp3& a) { return fp_is_square(fp3_norm(a)); }
 // sqrt in Fp3 through the norm: with e = p^2 + p + 1 (odd), a^e = N(a) in Fp and
 //   sqrt(a) = a^((e+1)/2) / sqrt(N(a)),   a^((e+1)/2) = Frob(a^((p+1)/2)) * a,  (p+1)/2 = 2^31 (2^32-1) + 1
-SB_DEV bool fp3_sqrt(const fp3& a, fp3& out) {
-    if (fp3_is_zero(a)) {
-        out = a;
-        return true;
-    }
+SB_DEV_NOINLINE fp3 fp3_sqrt_or_none(fp3 a) {
+    if (fp3_is_zero(a)) return a;
     fp_t s;
-    if (!fp_sqrt(fp3_norm(a), s)) return false;
+    if (!fp_sqrt(fp3_norm(a), s)) return fp3{{FP_NONE, 0, 0}};
     // c = a^(2^32 - 1)
     fp3 t2 = fp3_mul(fp3_sqr(a), a);
     fp3 t4 = fp3_mul(fp3_sqr_n(t2, 2), t2);
@@ -290,7 +292,12 @@ SB_DEV bool fp3_sqrt(const fp3& a, fp3& out) {
     const fp_t w = 0xfffffffe00000001ULL;  // FP_OMEGA3: v^p = w v
     const fp_t w2 = fp_sqr(w);
     fp3 f = fp3{{c.c[0], fp_mul(c.c[1], w), fp_mul(c.c[2], w2)}};  // Frobenius
-    out = fp3_scale(fp3_mul(f, a), fp_inv(s));
+    return fp3_scale(fp3_mul(f, a), fp_inv(s));
+}
+SB_DEV bool fp3_sqrt(const fp3& a, fp3& out) {
+    fp3 r = fp3_sqrt_or_none(a);
+    if (r.c[0] == FP_NONE) return false;
+    out = r;
     return true;
 }
 

@@ -45,26 +45,59 @@ SB_DEV void rescue_mds_ark(fp_t* s, int ark_row) {
         }
         // value = lo + hi * 2^32 < 2^74
         uint64_t mid = (lo >> 32) + hi;  // weight 2^32, < 2^43
-        fp_t r = fp_reduce160((uint32_t)lo, (uint32_t)mid, (uint32_t)(mid >> 32), 0, 0);
+        fp_t r = fp_reduce96((uint32_t)lo, (uint32_t)mid, (uint32_t)(mid >> 32));
         t[i] = fp_add(r, SB_ARK(ark_row * 12 + i));
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = t[i];
 }
 
-// x^(1/7) = x^0x92492491b6db6db7: sliding pattern "100" x 10, then "110" x 10 + "111":
-// 63 squarings + 9 multiplications.
+// x^(1/7) = x^0x92492491b6db6db7 = "100" x 10, "0", then "110" x 10 + "111" in binary:
+// 63 squarings + 9 multiplications, evaluated on LANES independent elements at once (instruction-
+// level parallelism) with rolled squaring loops (compact code: the whole round stays in the
+// instruction cache).
+template <int LANES>
+SB_DEV void sqr_n_lanes(fp_t* v, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+#pragma unroll
+        for (int l = 0; l < LANES; l++) v[l] = fp_sqr(v[l]);
+    }
+}
+template <int LANES>
+SB_DEV void rescue_inv_sbox_lanes(fp_t* x) {
+    fp_t t1[LANES], t2[LANES], t3[LANES], t6[LANES], w[LANES];
+#pragma unroll
+    for (int l = 0; l < LANES; l++) {
+        t1[l] = fp_sqr(x[l]);   // 10b
+        t2[l] = fp_sqr(t1[l]);  // 100b
+        w[l] = t2[l];
+    }
+    sqr_n_lanes<LANES>(w, 3);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) t3[l] = w[l] = fp_mul(w[l], t2[l]);  // 100100b
+    sqr_n_lanes<LANES>(w, 6);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul(w[l], t3[l]);  // (100)x4
+    fp_t t4[LANES];
+#pragma unroll
+    for (int l = 0; l < LANES; l++) t4[l] = w[l];
+    sqr_n_lanes<LANES>(w, 12);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul(w[l], t4[l]);  // (100)x8
+    sqr_n_lanes<LANES>(w, 6);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) t6[l] = w[l] = fp_mul(w[l], t3[l]);  // (100)x10
+    sqr_n_lanes<LANES>(w, 31);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul(fp_sqr(fp_mul(w[l], t6[l])), t6[l]);  // t7^2 * t6
+    sqr_n_lanes<LANES>(w, 2);
+#pragma unroll
+    for (int l = 0; l < LANES; l++) x[l] = fp_mul(w[l], fp_mul(fp_mul(t1[l], t2[l]), x[l]));
+}
 SB_DEV fp_t rescue_inv_sbox(fp_t x) {
-    fp_t t1 = fp_sqr(x);                          // 10b
-    fp_t t2 = fp_sqr(t1);                         // 100b
-    fp_t t3 = fp_mul(fp_sqr_n(t2, 3), t2);        // 100100b
-    fp_t t4 = fp_mul(fp_sqr_n(t3, 6), t3);        // (100)x4
-    fp_t t5 = fp_mul(fp_sqr_n(t4, 12), t4);       // (100)x8
-    fp_t t6 = fp_mul(fp_sqr_n(t5, 6), t3);        // (100)x10
-    fp_t t7 = fp_mul(fp_sqr_n(t6, 31), t6);       // (100)x10 0 (100)x10
-    fp_t a = fp_sqr_n(fp_mul(fp_sqr(t7), t6), 2);
-    fp_t b = fp_mul(fp_mul(t1, t2), x);           // x^7
-    return fp_mul(a, b);
+    rescue_inv_sbox_lanes<1>(&x);
+    return x;
 }
 
 SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
@@ -74,11 +107,8 @@ SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
         for (int i = 0; i < 12; i++) s[i] = rescue_sbox(s[i]);
         rescue_mds_ark(s, 2 * r);
         // inverse S-box, 4 independent chains at a time for ILP without blowing up registers
-#pragma unroll 1
-        for (int g = 0; g < 12; g += 4) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) s[g + i] = rescue_inv_sbox(s[g + i]);
-        }
+        rescue_inv_sbox_lanes<6>(s);
+        rescue_inv_sbox_lanes<6>(s + 6);
         rescue_mds_ark(s, 2 * r + 1);
     }
 }

@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(INGEST_THREADS) k_ingest(size_t n, const uint8
 // K2: Signature::verify, one signature per thread
 // ------------------------------------------------------------------------------------------------
 static constexpr int VERIFY_THREADS = 128;
-__global__ void __launch_bounds__(VERIFY_THREADS) k_verify(soa_batch in, const uint8_t* __restrict__ msgs,
+#ifndef VERIFY_MIN_BLOCKS
+#define VERIFY_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(soa_batch in, const uint8_t* __restrict__ msgs,
                                                            const uint64_t* __restrict__ msg_off,
                                                            const uint64_t* __restrict__ gtab,
                                                            uint8_t* __restrict__ verdicts) {
