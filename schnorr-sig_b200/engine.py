@@ -133,6 +133,28 @@ class Engine:
                     "verify_batch")
         return verdict.value, lhs, rhs
 
+    def batch_partial(self, sigs81, pk96, pk_inf, msgs, off, rand32):
+        """This rank's share of a batch: host arrays in, the 192-byte partial out (multi-GPU form).
+        torch is used only to hold the device buffers."""
+        import torch
+        sigs81, pk96, msgs, rand32 = _u8(sigs81, 81), _u8(pk96, 96), _u8(msgs), _u8(rand32, 32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = sigs81.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        dev = torch.device("cuda", self.device)
+        part = torch.zeros(192, dtype=torch.uint8, device=dev)
+        if n == 0:
+            self.batch_partial_dev(0, None, None, None, None, None, None, part)
+        else:
+            def up(a):
+                return torch.from_numpy(np.ascontiguousarray(a)).to(dev) if a.size else torch.zeros(16, dtype=torch.uint8, device=dev)
+            t = [up(sigs81), up(pk96), None if pk_inf is None else up(_u8(pk_inf)), up(msgs),
+                 torch.from_numpy(off.view(np.int64)).to(dev), up(rand32)]
+            torch.cuda.synchronize(dev)
+            self.batch_partial_dev(n, t[0], t[1], t[2], t[3], t[4], t[5], part)
+        self.synchronize()
+        return part.cpu().numpy()
+
     def batch_finish(self, partials192):
         partials192 = _u8(partials192, 192)
         verdict = C.c_int(-1)
