@@ -50,3 +50,16 @@ def test_full_size_fault_pattern(log2n, msg_len):
     bad = w["sigs"][sl].copy()
     bad[nb // 2, 49] ^= 1
     assert eng.verify_batch(bad, w["pk"][sl], w["inf"][sl], w["blob"][:nb * msg_len], boff, w["rand"][sl])[0] == 2
+
+
+def test_cpp_facade_example_runs():
+    """The C++ host facade (include/schnorr_b200.hpp) over the C ABI: sign, verify, batch, codecs."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "verify_example")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
