@@ -247,6 +247,67 @@ SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab)
     return acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-doubling ("Yao" / bucket) evaluation of the two variable-base products of a verification:
+// the subgroup check [q]P and the challenge product h*P use the SAME chain D_i = 16^i P
+// (252 doublings instead of 2 x 254), each scalar in signed 4-bit windows d_i in [-8, 8]:
+//     B[|d_i|] += sign(d_i) * D_i        then        k*P = sum_{m=1..8} m * B[m]   (14 additions)
+// q's digits are constants (warp-uniform additions); h's digits are per thread.
+#if defined(__CUDACC__)
+__constant__ int8_t c_q_sw4[64];  // CHEETAH_Q_SW4, filled at context creation
+#define SB_QSW4(i) c_q_sw4[i]
+#else
+#define SB_QSW4(i) CHEETAH_Q_SW4[i]
+#endif
+
+// k < 2^255  ->  64 signed digits, k = sum d_i 16^i, |d_i| <= 8
+SB_DEV void recode_signed_w4(const scalar& k, int8_t* d /*64*/) {
+    int carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        int raw = (int)((k.l[i >> 3] >> (4 * (i & 7))) & 15) + carry;
+        carry = raw > 8;
+        d[i] = (int8_t)(carry ? raw - 16 : raw);
+    }
+}
+// out = sum_{m=1..8} m * B[m-1]
+SB_DEV void bucket_aggregate(const jac_pt* B, jac_pt* out) {
+    jac_pt running = B[7];
+    *out = B[7];
+#pragma unroll 1
+    for (int m = 6; m >= 0; m--) {
+        jac_add_mem(&running, &B[m], false);
+        jac_add_mem(out, &running, false);
+    }
+}
+// returns [q]P == O (AffinePoint::is_torsion_free, src/signature.rs:182) and writes h*P
+SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) {
+    jac_pt Bq[8], Bh[8];
+#pragma unroll 1
+    for (int b = 0; b < 8; b++) {
+        Bq[b] = jac_identity();
+        Bh[b] = jac_identity();
+    }
+    int8_t hd[64];
+    recode_signed_w4(h, hd);
+    jac_pt D = P;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        if (i != 0) {
+#pragma unroll 1
+            for (int s = 0; s < 4; s++) jac_dbl_mem(&D);
+        }
+        int dq = SB_QSW4(i);
+        if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) - 1], &D, dq < 0);  // warp-uniform
+        int dh = hd[i];
+        if (dh != 0) jac_add_mem(&Bh[(dh < 0 ? -dh : dh) - 1], &D, dh < 0);
+    }
+    jac_pt tq;
+    bucket_aggregate(Bq, &tq);
+    bucket_aggregate(Bh, hP);
+    return jac_is_identity(tq);
+}
+
 // AffinePoint::from_compressed (src/batch.rs:104, src/public.rs:55): 48 bytes of x + flag byte
 // (bit 7 infinity, bit 6 "y is the lexicographically largest root", other bits must be 0).
 // x arrives already split into limbs; returns false when the record does not decode.

@@ -28,15 +28,29 @@ typedef uint64_t fp_t;
 static constexpr uint64_t FP_P = 0xffffffff00000001ULL;
 static constexpr uint64_t FP_EPS = 0xffffffffULL;  // 2^64 mod p
 
-SB_DEV fp_t fp_add(fp_t a, fp_t b) {
-    uint64_t s = a + b;
-    bool over = (s < a) | (s >= FP_P);
-    return over ? s + FP_EPS : s;  // s - p == s + 2^32 - 1 (mod 2^64)
-}
+// a - b for a canonical and b <= p: one borrow chain, then "borrowed 2^64 == EPS too much" is undone
+// with the borrow mask (5 instructions, no compare/select).
 SB_DEV fp_t fp_sub(fp_t a, fp_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32), d0, d1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(d0), "=&r"(d1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)d1 << 32) | d0;
+#else
     uint64_t d = a - b;
     return (a < b) ? d - FP_EPS : d;  // d + p == d - (2^32 - 1) (mod 2^64)
+#endif
 }
+// a + b = a - (p - b); p - b is in [1, p] and fp_sub accepts a subtrahend equal to p
+SB_DEV fp_t fp_add(fp_t a, fp_t b) { return fp_sub(a, FP_P - b); }
 SB_DEV fp_t fp_neg(fp_t a) { return a ? FP_P - a : 0; }
 SB_DEV fp_t fp_dbl(fp_t a) { return fp_add(a, a); }
 

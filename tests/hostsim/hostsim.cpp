@@ -142,6 +142,14 @@ API void hs_double_base(const uint8_t* p96, int inf, const uint8_t* h32, const u
     build_odd_table(T, load_pt(p96, inf));
     store_aff(double_base_mul(T, ldsc(h32), ldsc(e32), g_gtab.data()), out96, out_inf);
 }
+// shared-doubling core: returns the subgroup verdict and h*P
+API int hs_torsion_check_and_mul(const uint8_t* p96, int inf, const uint8_t* h32, uint8_t* out96, int* out_inf) {
+    jac_pt r;
+    bool tf = torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r);
+    store_aff(r, out96, out_inf);
+    return tf;
+}
+API void hs_recode_signed_w4(const uint8_t* k, int8_t* digits64) { recode_signed_w4(ldsc(k), digits64); }
 API int hs_decompress(const uint8_t* in49, uint8_t* out96, int* out_inf) {
     fp6 x;
     memcpy(x.c, in49, 48);

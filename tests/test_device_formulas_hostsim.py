@@ -238,3 +238,31 @@ def test_verify_one_matches_oracle_verdicts(hostsim):
         mb = np.frombuffer(m, dtype=np.uint8).copy() if m else np.zeros(1, dtype=np.uint8)
         got = hostsim.hs_verify_one(p(sigs[i].copy()), p(pk[i].copy()), 0, p(mb), C.c_uint64(len(m)))
         assert got == want[i]
+
+
+def test_shared_doubling_core(hostsim):
+    """torsion_check_and_mul: [q]P == O and h*P from one doubling chain, incl. adversarial keys."""
+    rng = np.random.default_rng(21)
+    d = np.zeros(64, dtype=np.int8)
+    for k in [0, 1, 8, 9, 15, 16, o.Q - 1, 2**255 - 1] + [int_le(s) for s in rand_scalars(rng, 40)]:
+        K = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy()
+        hostsim.hs_recode_signed_w4(p(K), p(d))
+        assert all(abs(int(x)) <= 8 for x in d) and sum(int(x) << (4 * i) for i, x in enumerate(d)) == k
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    n = o.COFACTOR * o.Q
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+    pts = [G, o.pt_mul(G, 12345), kat, o.pt_mul(kat, n // 2), o.pt_mul(kat, n // 5), o.pt_mul(kat, n // 10),
+           o.pt_add(G, o.pt_mul(kat, n // 2)), o.pt_mul(kat, o.Q)]
+    hs = [0, 1, 2, o.Q - 1, 0x8888888888888888, int_le(rand_scalars(rng, 1)[0])]
+    pts = [pt for pt in pts if pt is not o.INF]      # n/5 * KAT is the identity: KAT's order has no factor 5
+    assert len(pts) >= 6
+    for pt in pts:
+        for h in hs:
+            H = np.frombuffer(h.to_bytes(32, "little"), dtype=np.uint8).copy()
+            tf = hostsim.hs_torsion_check_and_mul(p(pt_to96(pt)), 0, p(H), p(out), C.byref(oi))
+            assert bool(tf) == o.is_torsion_free(pt)
+            assert (o.INF if oi.value else pt_from96(out)) == o.pt_mul(pt, h)
+    H = np.frombuffer((77).to_bytes(32, "little"), dtype=np.uint8).copy()
+    assert hostsim.hs_torsion_check_and_mul(p(KAT96), 1, p(H), p(out), C.byref(oi)) == 1 and oi.value == 1

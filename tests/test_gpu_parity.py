@@ -99,11 +99,12 @@ def test_verify_adversarial_public_keys(eng):
     n = o.COFACTOR * o.Q
     pk, inf = w["pk"].copy(), w["inf"].copy()
     pk[0] = pt_to96(o.pt_mul(kat, n // 2))                                     # order 2 (y = 0)
-    pk[1] = pt_to96(o.pt_mul(kat, n // 5))                                     # order 5
-    pk[2] = pt_to96(o.pt_mul(kat, n // 10))                                    # order 10
+    pk[1] = pt_to96(o.pt_mul(kat, n // 29))                                    # order 29
+    pk[2] = pt_to96(o.pt_mul(kat, n // 58))                                    # order 58
     pk[3] = pt_to96(o.pt_add(o.generator(), o.pt_mul(kat, n // 2)))            # order 2q
     pk[4] = pt_to96(o.pt_mul(kat, o.Q))                                        # order = cofactor
     inf[5] = 1                                                                 # identity key
+    assert all(pk[i].any() for i in range(5))                                  # none of them is the identity
     got = eng.verify_many(w["sigs"], pk, inf, w["blob"], w["off"])
     want = cref.verify_many(w["sigs"], pk, inf, w["blob"], w["off"], 4)
     assert np.array_equal(got, want)
