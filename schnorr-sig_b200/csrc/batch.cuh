@@ -6,9 +6,10 @@
 //   k_batch_prepare   K3: per signature: challenge hash, h_i mod q, s_i e_i, s_i h_i, decompress R_i,
 //                     negate P_i -> 2n affine points + 2n scalars
 //   k_msm_count / k_msm_scatter   signed c-bit digits -> counting sort of point indices by bucket
-//   k_msm_bucket_sum  one bucket per thread, mixed additions of its (sorted) points
+//   k_msm_segment_sum fixed-size segments of the sorted list per thread, mixed additions; buckets that
+//                     straddle segments are completed by k_msm_segment_fixup (robust to skewed buckets)
 //   k_msm_window_sum  running-sum reduction of bucket chunks + chunk offsets
-//   k_msm_window_fold per-window total
+//   k_msm_window_fold per-window total: one warp per window, warp-shuffle tree of point additions
 //   k_msm_horner      sum_k 2^(ck) W_k  -> one Jacobian partial per GPU
 //   k_batch_finish    adds the per-GPU partials, (sum lin) * G, x-only comparison
 // The bucket sums are order-independent group elements, so the atomics-based (non-deterministic)
@@ -202,36 +203,89 @@ __device__ __forceinline__ void load_affine(const uint64_t* __restrict__ pts, si
     y = fp6{{d.x, d.y, e.x, e.y, f.x, f.y}};
 }
 
-// one bucket per thread
-__global__ void __launch_bounds__(128) k_msm_bucket_sum(const uint64_t* __restrict__ pts, msm_plan pl,
-                                                        const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ counts,
-                                                        const uint32_t* __restrict__ sorted, jac_pt* __restrict__ buckets) {
+// Bucket accumulation by fixed-size SEGMENTS of the sorted list (robust to skewed bucket sizes: the
+// sparse top window, repeated randomisers, adversarial scalars).  Thread t owns positions
+// [t*T, (t+1)*T) of `sorted`; it walks them bucket by bucket.  A bucket that lies entirely inside
+// the segment is written directly (sole writer); a bucket that crosses a segment boundary leaves a
+// partial sum (head: the bucket began before the segment; tail: it continues after) that
+// k_msm_segment_fixup adds up.  Empty buckets keep the zero fill (Z = 0 = identity).
+struct seg_partial {
+    jac_pt pt;
+    int32_t slot;  // -1 = unused
+    int32_t pad[3];
+};
+__device__ __forceinline__ size_t bucket_of_slot(const msm_plan& pl, uint32_t slot) {
+    uint32_t k = slot / (uint32_t)(pl.B + 1), b = slot % (uint32_t)(pl.B + 1);
+    return (size_t)k * pl.B + (b - 1);
+}
+__global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restrict__ pts, msm_plan pl, uint32_t nslots,
+                                                         uint32_t T, const uint32_t* __restrict__ offsets,
+                                                         const uint32_t* __restrict__ counts,
+                                                         const uint32_t* __restrict__ sorted, jac_pt* __restrict__ buckets,
+                                                         seg_partial* __restrict__ parts /*[nseg][2]*/) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)pl.K * pl.B;
-    if (t >= total) return;
-    int k = (int)(t / pl.B), b = (int)(t % pl.B) + 1;
-    size_t slot = (size_t)k * (pl.B + 1) + b;
-    uint32_t beg = offsets[slot], cnt = counts[slot];
-    jac_pt acc = jac_identity();
-    for (uint32_t u = 0; u < cnt; u++) {
-        uint32_t v = sorted[beg + u];
-        fp6 x, y;
-        load_affine(pts, v & 0x7fffffffu, x, y);
-        if (v >> 31) y = fp6_neg(y);
-        acc = jac_madd(acc, x, y, false);
+    uint32_t M = offsets[nslots - 1] + counts[nslots - 1];
+    uint64_t lo64 = (uint64_t)t * T;
+    parts[2 * t + 0].slot = -1;
+    parts[2 * t + 1].slot = -1;
+    if (lo64 >= M) return;
+    uint32_t lo = (uint32_t)lo64, hi = lo + T < M ? lo + T : M;
+    // last slot whose offset is <= lo
+    uint32_t a = 0, b = nslots;  // invariant: offsets[a] <= lo < offsets[b] (b = nslots: +inf)
+    while (b - a > 1) {
+        uint32_t m = (a + b) >> 1;
+        if (offsets[m] <= lo) a = m; else b = m;
     }
-    buckets[t] = acc;
+    uint32_t s = a, beg_s = offsets[s], end_s = beg_s + counts[s];
+    jac_pt acc = jac_identity();
+    for (uint32_t pos = lo; pos < hi; pos++) {
+        if (pos >= end_s) {
+            // flush bucket s (it ended inside this segment) and move to the bucket holding pos
+            if (beg_s >= lo) buckets[bucket_of_slot(pl, s)] = acc;          // complete: began and ended here
+            else { parts[2 * t + 0].pt = acc; parts[2 * t + 0].slot = (int32_t)s; }   // head partial
+            acc = jac_identity();
+            do { s++; beg_s = offsets[s]; end_s = beg_s + counts[s]; } while (pos >= end_s);
+        }
+        uint32_t v = sorted[pos];
+        jac_madd_mem(&acc, pts + (size_t)(v & 0x7fffffffu) * 12, (v >> 31) != 0, false);
+    }
+    bool began_here = beg_s >= lo, ends_here = end_s <= hi;
+    if (began_here && ends_here) buckets[bucket_of_slot(pl, s)] = acc;
+    else if (!began_here) { parts[2 * t + 0].pt = acc; parts[2 * t + 0].slot = (int32_t)s; }   // head (maybe whole segment)
+    else { parts[2 * t + 1].pt = acc; parts[2 * t + 1].slot = (int32_t)s; }                     // tail
+}
+// one thread per slot: buckets that straddle segment boundaries are the sum of their partials
+__global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t nslots, uint32_t T,
+                                                           const uint32_t* __restrict__ offsets,
+                                                           const uint32_t* __restrict__ counts,
+                                                           const seg_partial* __restrict__ parts, jac_pt* __restrict__ buckets) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    uint32_t cnt = counts[s];
+    if (cnt == 0) return;
+    uint32_t beg = offsets[s], end = beg + cnt;
+    uint32_t sa = beg / T, sb = (end - 1) / T;
+    if (sa == sb) return;  // written directly by its segment
+    jac_pt acc = jac_identity();
+    for (uint32_t g = sa; g <= sb; g++) {
+#pragma unroll 1
+        for (int w = 0; w < 2; w++) {
+            const seg_partial* p = &parts[2 * (size_t)g + w];
+            if (p->slot == (int32_t)s) jac_add_mem(&acc, &p->pt, false);
+        }
+    }
+    buckets[bucket_of_slot(pl, s)] = acc;
 }
 
 // small multiple m * P by double-and-add (m < 2^20)
-__device__ jac_pt jac_mul_small(const jac_pt& P, uint32_t m) {
+__device__ void jac_mul_small_mem(jac_pt* out, const jac_pt* P, uint32_t m) {
     jac_pt acc = jac_identity();
+#pragma unroll 1
     for (int bit = 19; bit >= 0; bit--) {
-        acc = jac_dbl(acc);
-        if ((m >> bit) & 1) acc = jac_add(acc, P);
+        jac_dbl_mem(&acc);
+        if ((m >> bit) & 1) jac_add_mem(&acc, P, false);
     }
-    return acc;
+    *out = acc;
 }
 
 // chunk t of window k covers buckets lo..lo+chunk_sz-1 (1-based ids): contributes
@@ -244,28 +298,52 @@ __global__ void __launch_bounds__(64) k_msm_window_sum(msm_plan pl, const jac_pt
     int lo = ch * pl.chunk_sz + 1;
     const jac_pt* bk = buckets + (size_t)k * pl.B + (lo - 1);
     jac_pt running = jac_identity(), acc = jac_identity();
+#pragma unroll 1
     for (int b = pl.chunk_sz - 1; b >= 0; b--) {
-        running = jac_add(running, bk[b]);
-        acc = jac_add(acc, running);
+        jac_add_mem(&running, &bk[b], false);
+        jac_add_mem(&acc, &running, false);
     }
-    if (lo > 1) acc = jac_add(acc, jac_mul_small(running, (uint32_t)(lo - 1)));
+    if (lo > 1) {
+        jac_pt m;
+        jac_mul_small_mem(&m, &running, (uint32_t)(lo - 1));
+        jac_add_mem(&acc, &m, false);
+    }
     chunk_out[t] = acc;
 }
-__global__ void k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out, jac_pt* __restrict__ windows) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= pl.K) return;
+// one warp per window: lanes add strided chunk results, then a shuffle tree ("warp-shuffle bucket reduction")
+__device__ __forceinline__ jac_pt shfl_down_jac(const jac_pt& p, int delta) {
+    jac_pt r;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        r.X.c[c] = __shfl_down_sync(0xffffffffu, p.X.c[c], delta);
+        r.Y.c[c] = __shfl_down_sync(0xffffffffu, p.Y.c[c], delta);
+        r.Z.c[c] = __shfl_down_sync(0xffffffffu, p.Z.c[c], delta);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out,
+                                                        jac_pt* __restrict__ windows) {
+    int k = blockIdx.x, lane = threadIdx.x;
     jac_pt acc = jac_identity();
-    for (int ch = 0; ch < pl.chunks; ch++) acc = jac_add(acc, chunk_out[(size_t)k * pl.chunks + ch]);
-    windows[k] = acc;
+#pragma unroll 1
+    for (int ch = lane; ch < pl.chunks; ch += 32) jac_add_mem(&acc, &chunk_out[(size_t)k * pl.chunks + ch], false);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        jac_pt o = shfl_down_jac(acc, d);
+        jac_add_mem(&acc, &o, false);
+    }
+    if (lane == 0) windows[k] = acc;
 }
 // partial192 = Jacobian point (18 u64) || partial scalar sum (4 u64) || bad flag (u64) || pad
 __global__ void k_msm_horner(msm_plan pl, const jac_pt* __restrict__ windows, const uint32_t* __restrict__ lin,
                              const int* __restrict__ bad, uint64_t* __restrict__ partial) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     jac_pt acc = windows[pl.K - 1];
+#pragma unroll 1
     for (int k = pl.K - 2; k >= 0; k--) {
-        for (int s = 0; s < pl.c; s++) acc = jac_dbl(acc);
-        acc = jac_add(acc, windows[k]);
+#pragma unroll 1
+        for (int s = 0; s < pl.c; s++) jac_dbl_mem(&acc);
+        jac_add_mem(&acc, &windows[k], false);
     }
 #pragma unroll
     for (int c = 0; c < 6; c++) {
@@ -296,7 +374,7 @@ __global__ void k_batch_finish(size_t np, const uint64_t* __restrict__ partials,
             t.Y.c[c] = p[6 + c];
             t.Z.c[c] = p[12 + c];
         }
-        acc = jac_add(acc, t);
+        jac_add_mem(&acc, &t, false);
         lin = sc_add(lin, sc_from_u64x4(p[18], p[19], p[20], p[21]));
         bad |= p[22] != 0;
     }
@@ -341,6 +419,13 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     if (int rc = ensure_scratch(ctx, SL_K, sizeof(jac_pt) * ((size_t)pl.K * pl.B + (size_t)pl.K * pl.chunks + pl.K), &d_buckets))
         return rc;
     if (int rc = ensure_scratch(ctx, SL_L, 64, &d_small)) return rc;
+    // segment length: 32 entries per thread, longer for very large batches (bounds the partial arrays)
+    size_t max_entries = npts * (size_t)pl.K;
+    uint32_t T = 32;
+    while ((max_entries + T - 1) / T > ((size_t)1 << 20)) T *= 2;
+    size_t nseg = ((max_entries + T - 1) / T + 127) / 128 * 128;
+    void* d_parts;
+    if (int rc = ensure_scratch(ctx, SL_I, nseg * 2 * sizeof(seg_partial), &d_parts)) return rc;
     uint32_t* counts = (uint32_t*)d_cnt;
     uint32_t* offsets = counts + nslots;
     uint32_t* cursor = offsets + nslots;
@@ -363,14 +448,17 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     k_msm_count<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, counts);
     k_exclusive_scan<<<1, 1024, 0, st>>>(counts, nslots, offsets);
     k_msm_scatter<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, offsets, cursor, (uint32_t*)d_sorted);
+    CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, sizeof(jac_pt) * (size_t)pl.K * pl.B, st));   // Z = 0: identity
     cudaEventRecord(ctx->ev_k0, st);
-    k_msm_bucket_sum<<<grid_for((size_t)pl.K * pl.B, 128), 128, 0, st>>>((uint64_t*)d_pts, pl, offsets, counts,
-                                                                         (uint32_t*)d_sorted, buckets);
+    k_msm_segment_sum<<<(unsigned)(nseg / 128), 128, 0, st>>>((uint64_t*)d_pts, pl, (uint32_t)nslots, T, offsets, counts,
+                                                              (uint32_t*)d_sorted, buckets, (seg_partial*)d_parts);
     cudaEventRecord(ctx->ev_k1, st);
+    k_msm_segment_fixup<<<grid_for(nslots, 128), 128, 0, st>>>(pl, (uint32_t)nslots, T, offsets, counts,
+                                                               (seg_partial*)d_parts, buckets);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, 64), 64, 0, st>>>(pl, buckets, chunk_out);
-    k_msm_window_fold<<<grid_for((size_t)pl.K, 32), 32, 0, st>>>(pl, chunk_out, windows);
+    k_msm_window_fold<<<pl.K, 32, 0, st>>>(pl, chunk_out, windows);
     k_msm_horner<<<1, 1, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
-    ctx->launches += 11;
+    ctx->launches += 12;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
 }
