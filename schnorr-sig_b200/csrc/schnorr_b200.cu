@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(INGEST_THREADS) k_ingest(size_t n, const uint8
 // ------------------------------------------------------------------------------------------------
 // K2: Signature::verify, one signature per thread
 // ------------------------------------------------------------------------------------------------
-static constexpr int VERIFY_THREADS = 128;
+#ifndef VERIFY_THREADS_N
+#define VERIFY_THREADS_N 128
+#endif
+static constexpr int VERIFY_THREADS = VERIFY_THREADS_N;
 #ifndef VERIFY_MIN_BLOCKS
 #define VERIFY_MIN_BLOCKS 2
 #endif
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint64_t* sink) {
         for (int k = 0; k < 8; k++) {
             asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
         }
-        b += (uint32_t)acc[0];
+        b += 3;
     }
     uint64_t s = 0;
 #pragma unroll
