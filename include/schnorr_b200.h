@@ -115,6 +115,12 @@ int schnorr_b200_decompress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *in49
 int schnorr_b200_compress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *pk96, const uint8_t *pk_inf,
                           uint8_t *out49);
 
+/* Test hook (no reference counterpart): raw device field operations so that the PTX arithmetic can be
+ * checked against the oracle on edge values.  a6, b6: n x 6 canonical limbs (host); out48: n x 48 u64 =
+ * fp6_mul(a,b) | fp6_sqr(a) | a+b | a-b | limb-wise a_k*b_k | limb-wise a_k^2 | fp6_inv(a) | limb-wise a_k^(1/7). */
+int schnorr_b200_debug_field_ops(schnorr_b200_ctx *ctx, size_t n, const uint64_t *a6, const uint64_t *b6,
+                                 uint64_t *out48);
+
 /* Integer-multiply roofline calibration: runs a register-resident chain of `iters` dependent-free
  * 32x32->64 multiply-adds per thread on a full grid and returns wide multiplies per second. */
 int schnorr_b200_imad_peak(schnorr_b200_ctx *ctx, int iters, double *wide_mul_per_s, double *elapsed_ms);

@@ -212,18 +212,89 @@ SB_DEV fp_t wide_reduce(const wide_acc& w) {
     return fp_reduce160(w.e0, x1, x2, x3, x4);
 }
 
-SB_DEV fp_t fp_mul(fp_t a, fp_t b) {
-    wide_acc w;
-    wide_zero(w);
-    wide_mac(w, a, b);
-    return wide_reduce(w);
+// ---- single products -----------------------------------------------------------------------------
+// Dedicated 64x64 multiply / square for the long exponentiation chains (Rescue S-boxes, inversions,
+// square roots): 4 (3) IMAD.WIDE, two carry adds and a 13-instruction reduction.  The *_nc forms
+// accept ANY 64-bit representatives and return a value < 2^64 that may be >= p ("not canonical"):
+// chains stay in that form and canonicalise once at the end (fp_canon).
+SB_DEV fp_t fp_canon(fp_t x) { return x >= FP_P ? x - FP_P : x; }
+
+SB_DEV fp_t fp_mul_nc(fp_t a, fp_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32), t0, t1;
+    asm("{\n\t"
+        ".reg .u32 p0, p1, p2, p3, m, m0, m1, c;\n\t"
+        "mul.lo.u32 p0, %2, %4;\n\t"
+        "mul.hi.u32 p1, %2, %4;\n\t"
+        "mul.lo.u32 p2, %3, %5;\n\t"
+        "mul.hi.u32 p3, %3, %5;\n\t"
+        "mad.lo.cc.u32 p1, %2, %5, p1;\n\t"
+        "madc.hi.cc.u32 p2, %2, %5, p2;\n\t"
+        "addc.u32 p3, p3, 0;\n\t"
+        "mad.lo.cc.u32 p1, %3, %4, p1;\n\t"
+        "madc.hi.cc.u32 p2, %3, %4, p2;\n\t"
+        "addc.u32 p3, p3, 0;\n\t"
+        "sub.cc.u32 %0, p0, p3;\n\t"      // (p1:p0) - p3          [2^96 == -1]
+        "subc.cc.u32 %1, p1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "sub.cc.u32 m0, 0, p2;\n\t"       // + p2 * (2^32 - 1)     [2^64 == 2^32 - 1]
+        "subc.u32 m1, p2, 0;\n\t"
+        "add.cc.u32 %0, %0, m0;\n\t"
+        "addc.cc.u32 %1, %1, m1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.u32 c, 0, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(t0), "=&r"(t1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)t1 << 32) | t0;
+#else
+    return (fp_t)(((unsigned __int128)a * b) % FP_P);
+#endif
 }
-SB_DEV fp_t fp_sqr(fp_t a) {
-    wide_acc w;
-    wide_zero(w);
-    wide_mac_sqr(w, a);
-    return wide_reduce(w);
+SB_DEV fp_t fp_sqr_nc(fp_t a) {
+#if defined(__CUDA_ARCH__)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), t0, t1;
+    asm("{\n\t"
+        ".reg .u32 p0, p1, p2, p3, c0, c1, c2, m, m0, m1, c;\n\t"
+        "mul.lo.u32 p0, %2, %2;\n\t"
+        "mul.hi.u32 p1, %2, %2;\n\t"
+        "mul.lo.u32 p2, %3, %3;\n\t"
+        "mul.hi.u32 p3, %3, %3;\n\t"
+        "mul.lo.u32 c0, %2, %3;\n\t"
+        "mul.hi.u32 c1, %2, %3;\n\t"
+        "shf.l.clamp.b32 c2, c1, 0, 1;\n\t"   // 2 * cross product (65 bits: c2:c1:c0)
+        "shf.l.clamp.b32 c1, c0, c1, 1;\n\t"
+        "shl.b32 c0, c0, 1;\n\t"
+        "add.cc.u32 p1, p1, c0;\n\t"
+        "addc.cc.u32 p2, p2, c1;\n\t"
+        "addc.u32 p3, p3, c2;\n\t"
+        "sub.cc.u32 %0, p0, p3;\n\t"
+        "subc.cc.u32 %1, p1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "sub.cc.u32 m0, 0, p2;\n\t"
+        "subc.u32 m1, p2, 0;\n\t"
+        "add.cc.u32 %0, %0, m0;\n\t"
+        "addc.cc.u32 %1, %1, m1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.u32 c, 0, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(t0), "=&r"(t1)
+        : "r"(a0), "r"(a1));
+    return ((uint64_t)t1 << 32) | t0;
+#else
+    return (fp_t)(((unsigned __int128)a * a) % FP_P);
+#endif
 }
+SB_DEV fp_t fp_mul(fp_t a, fp_t b) { return fp_canon(fp_mul_nc(a, b)); }
+SB_DEV fp_t fp_sqr(fp_t a) { return fp_canon(fp_sqr_nc(a)); }
 // a * k for a small constant k < 2^32
 SB_DEV fp_t fp_mul_small(fp_t a, uint32_t k) {
     uint64_t lo = (uint64_t)(uint32_t)a * k;
@@ -236,11 +307,12 @@ SB_DEV fp_t fp_mul_small(fp_t a, uint32_t k) {
 SB_DEV fp_t fp_mul7(fp_t a) { return fp_mul_small(a, 7); }
 
 // a^(2^n)
-SB_DEV fp_t fp_sqr_n(fp_t a, int n) {
+SB_DEV fp_t fp_sqr_n_nc(fp_t a, int n) {
 #pragma unroll 1
-    for (int i = 0; i < n; i++) a = fp_sqr(a);
+    for (int i = 0; i < n; i++) a = fp_sqr_nc(a);
     return a;
 }
+SB_DEV fp_t fp_sqr_n(fp_t a, int n) { return fp_canon(fp_sqr_n_nc(a, n)); }
 // a^-1 = a^(p-2),  p - 2 = 0xfffffffeffffffff = (2^31 - 1) << 33 | (2^32 - 1): 63 squarings + 10 multiplications
 SB_DEV_NOINLINE fp_t fp_inv(fp_t a) {
     // t_k = a^(2^k - 1)

@@ -23,11 +23,12 @@ __constant__ uint64_t c_ark[2 * RESCUE_ROUNDS * 12];  // filled from RESCUE_ARK 
 #endif
 
 // x^7
+// (result not canonical: the MDS layer that follows accepts any 64-bit representative)
 SB_DEV fp_t rescue_sbox(fp_t x) {
-    fp_t x2 = fp_sqr(x);
-    fp_t x3 = fp_mul(x2, x);
-    fp_t x4 = fp_sqr(x2);
-    return fp_mul(x3, x4);
+    fp_t x2 = fp_sqr_nc(x);
+    fp_t x3 = fp_mul_nc(x2, x);
+    fp_t x4 = fp_sqr_nc(x2);
+    return fp_mul_nc(x3, x4);
 }
 
 // y = M * s + k  with M circulant, entries <= 26: the low and high 32-bit halves of the inputs are
@@ -61,7 +62,7 @@ SB_DEV void sqr_n_lanes(fp_t* v, int n) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) {
 #pragma unroll
-        for (int l = 0; l < LANES; l++) v[l] = fp_sqr(v[l]);
+        for (int l = 0; l < LANES; l++) v[l] = fp_sqr_nc(v[l]);
     }
 }
 template <int LANES>
@@ -69,35 +70,35 @@ SB_DEV void rescue_inv_sbox_lanes(fp_t* x) {
     fp_t t1[LANES], t2[LANES], t3[LANES], t6[LANES], w[LANES];
 #pragma unroll
     for (int l = 0; l < LANES; l++) {
-        t1[l] = fp_sqr(x[l]);   // 10b
-        t2[l] = fp_sqr(t1[l]);  // 100b
+        t1[l] = fp_sqr_nc(x[l]);   // 10b
+        t2[l] = fp_sqr_nc(t1[l]);  // 100b
         w[l] = t2[l];
     }
     sqr_n_lanes<LANES>(w, 3);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) t3[l] = w[l] = fp_mul(w[l], t2[l]);  // 100100b
+    for (int l = 0; l < LANES; l++) t3[l] = w[l] = fp_mul_nc(w[l], t2[l]);  // 100100b
     sqr_n_lanes<LANES>(w, 6);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) w[l] = fp_mul(w[l], t3[l]);  // (100)x4
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul_nc(w[l], t3[l]);  // (100)x4
     fp_t t4[LANES];
 #pragma unroll
     for (int l = 0; l < LANES; l++) t4[l] = w[l];
     sqr_n_lanes<LANES>(w, 12);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) w[l] = fp_mul(w[l], t4[l]);  // (100)x8
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul_nc(w[l], t4[l]);  // (100)x8
     sqr_n_lanes<LANES>(w, 6);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) t6[l] = w[l] = fp_mul(w[l], t3[l]);  // (100)x10
+    for (int l = 0; l < LANES; l++) t6[l] = w[l] = fp_mul_nc(w[l], t3[l]);  // (100)x10
     sqr_n_lanes<LANES>(w, 31);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) w[l] = fp_mul(fp_sqr(fp_mul(w[l], t6[l])), t6[l]);  // t7^2 * t6
+    for (int l = 0; l < LANES; l++) w[l] = fp_mul_nc(fp_sqr_nc(fp_mul_nc(w[l], t6[l])), t6[l]);  // t7^2 * t6
     sqr_n_lanes<LANES>(w, 2);
 #pragma unroll
-    for (int l = 0; l < LANES; l++) x[l] = fp_mul(w[l], fp_mul(fp_mul(t1[l], t2[l]), x[l]));
+    for (int l = 0; l < LANES; l++) x[l] = fp_mul_nc(w[l], fp_mul_nc(fp_mul_nc(t1[l], t2[l]), x[l]));
 }
 SB_DEV fp_t rescue_inv_sbox(fp_t x) {
     rescue_inv_sbox_lanes<1>(&x);
-    return x;
+    return fp_canon(x);
 }
 
 SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {

@@ -354,6 +354,36 @@ __global__ void __launch_bounds__(128) k_gtab_fill(const jac_pt* __restrict__ ba
 }
 
 // ------------------------------------------------------------------------------------------------
+// test hook: raw field operations on the device (the PTX paths cannot be exercised on a CPU box)
+//   out[i] = { fp6_mul(a,b) (6) | fp6_sqr(a) (6) | a+b (6) | a-b (6) | limb-wise fp_mul (6) | limb-wise fp_sqr(a) (6) |
+//              fp6_inv(a) (6) | limb-wise rescue x^(1/7) of a (6) }
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_debug_field(size_t n, const uint64_t* __restrict__ a6, const uint64_t* __restrict__ b6,
+                                                     uint64_t* __restrict__ out48) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp6 a, b;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        a.c[k] = a6[i * 6 + k];
+        b.c[k] = b6[i * 6 + k];
+    }
+    fp6 m = fp6_mul(a, b), q = fp6_sqr(a), ad = fp6_add(a, b), su = fp6_sub(a, b), iv = fp6_inv(a);
+    uint64_t* o = out48 + i * 48;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        o[k] = m.c[k];
+        o[6 + k] = q.c[k];
+        o[12 + k] = ad.c[k];
+        o[18 + k] = su.c[k];
+        o[24 + k] = fp_mul(a.c[k], b.c[k]);
+        o[30 + k] = fp_sqr(a.c[k]);
+        o[36 + k] = iv.c[k];
+        o[42 + k] = rescue_inv_sbox(a.c[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K6: integer-multiply roofline calibration.  8 independent accumulator chains per thread of
 // 32x32+64 -> 64 multiply-adds (IMAD.WIDE.U32), no memory traffic.
 // ------------------------------------------------------------------------------------------------
@@ -658,6 +688,23 @@ int schnorr_b200_compress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* pk96, 
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out49, d_out, n * 49, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- test hook -------------------------------------------------------------------------------
+int schnorr_b200_debug_field_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t* a6, const uint64_t* b6, uint64_t* out48) {
+    if (!ctx || (n && (!a6 || !b6 || !out48))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_a, *d_b, *d_o;
+    if (int rc = stage_in(ctx, SL_D, a6, n * 48, &d_a)) return rc;
+    if (int rc = stage_in(ctx, SL_E, b6, n * 48, &d_b)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n * 48 * 8, &d_o)) return rc;
+    k_debug_field<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint64_t*)d_a, (uint64_t*)d_b, (uint64_t*)d_o);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out48, d_o, n * 48 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SCHNORR_B200_OK;
 }

@@ -200,6 +200,14 @@ class Engine:
         self._check(self._L.schnorr_b200_compress(self._h, n, _ptr(pk96), _ptr(inf), _ptr(out)), "compress")
         return out
 
+    def debug_field_ops(self, a6, b6):
+        """Test hook: device field operations on n pairs of Fp6 elements -> [n, 8, 6] uint64."""
+        a6 = np.ascontiguousarray(a6, dtype=np.uint64).reshape(-1, 6)
+        b6 = np.ascontiguousarray(b6, dtype=np.uint64).reshape(-1, 6)
+        out = np.zeros((a6.shape[0], 8, 6), dtype=np.uint64)
+        self._check(self._L.schnorr_b200_debug_field_ops(self._h, a6.shape[0], _ptr(a6), _ptr(b6), _ptr(out)), "debug_field_ops")
+        return out
+
     def imad_peak(self, iters=1 << 16):
         w = C.c_double(0)
         ms = C.c_double(0)
