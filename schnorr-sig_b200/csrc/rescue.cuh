@@ -107,9 +107,9 @@ SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = rescue_sbox(s[i]);
         rescue_mds_ark(s, 2 * r);
-        // inverse S-box, 4 independent chains at a time for ILP without blowing up registers
-        rescue_inv_sbox_lanes<6>(s);
-        rescue_inv_sbox_lanes<6>(s + 6);
+        // inverse S-box: 6 independent chains at a time (ILP), one rolled copy of the code for both halves
+#pragma unroll 1
+        for (int g = 0; g < 12; g += 6) rescue_inv_sbox_lanes<6>(s + g);
         rescue_mds_ark(s, 2 * r + 1);
     }
 }
