@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--msg-len", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true", help="skip the hash / batch side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--batch-log2n", type=int, default=None,
+                    help="signatures per GPU of the batch side measurement (default 16 at 1 GPU = configs[3], "
+                         "21 at N > 1 = configs[4]: 2^24 over 8 GPUs)")
     return ap.parse_args()
 
 
@@ -154,11 +157,34 @@ def run_reference(args):
                        "signatures_per_step": s["n"]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": s["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL prints its version banner) must not pollute stdout: fd 1 is pointed at stderr and
+    the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
     args = parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -327,7 +353,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -351,14 +377,16 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
     out["hash"] = {"metric": "rescue_hash_message_per_sec", "value": world * n / (hms * 1e-3), "n_per_gpu": n, "msg_len": L,
                    "ms": hms, "roofline_frac_imad": (n * W_PER_HASH_L8 / (hms * 1e-3)) / peak_w if L == 8 else None}
     # K3/K4: one batch of nb signatures per GPU, partial MSM per rank + one small gather + finish on rank 0
-    nb = min(n, 1 << 16)
-    h_rand = hin["rand"][:nb]
-    good = hin  # valid signatures: regenerate (the main arrays carry injected faults)
+    import schnorr_sig_b200 as sb
+    blog = args.batch_log2n if args.batch_log2n is not None else (16 if world == 1 else 21)
+    nb = 1 << blog
+    bin_ = hin if nb <= n else sb.synth.host_inputs(sb.synth.DEFAULT_SEED + 1, nb, L, shard=rank)
+    h_rand = bin_["rand"][:nb]
     with torch.cuda.stream(stream):
-        d_sk = torch.from_numpy(hin["sk"][:nb]).to(dev)
-        d_nonce = torch.from_numpy(hin["nonce"][:nb]).to(dev)
-        gb = torch.from_numpy(hin["blob"][:nb * L]).to(dev) if L else torch.zeros(16, dtype=torch.uint8, device=dev)
-        goff = d_off[:nb + 1].contiguous()
+        d_sk = torch.from_numpy(bin_["sk"][:nb]).to(dev)
+        d_nonce = torch.from_numpy(bin_["nonce"][:nb]).to(dev)
+        gb = torch.from_numpy(bin_["blob"][:nb * L]).to(dev) if L else torch.zeros(16, dtype=torch.uint8, device=dev)
+        goff = torch.from_numpy(bin_["off"][:nb + 1].view(np.int64)).to(dev)
         gpk = torch.empty((nb, 96), dtype=torch.uint8, device=dev)
         ginf = torch.zeros(nb, dtype=torch.uint8, device=dev)
         gsig = torch.empty((nb, 81), dtype=torch.uint8, device=dev)
@@ -396,12 +424,20 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     bms = float(t.item())
     verdict = int(res[0].item()) if rank == 0 else None
+    # invalid-signature injection: one corrupted signature on the LAST rank must fail the lot
+    with torch.cuda.stream(stream):
+        if rank == world - 1:
+            gsig[nb // 2, 49] ^= 1
+        batch_once()
+        torch.cuda.synchronize(dev)
+    verdict_bad = int(res[0].item()) if rank == 0 else None
     out["batch"] = {"metric": "schnorr_batch_verified_signatures_per_sec", "value": world * nb / (bms * 1e-3),
                     "signatures_per_gpu": nb, "ms": bms, "verdict": verdict,
+                    "verdict_with_one_corrupted_signature_on_last_rank": verdict_bad,
                     "roofline_frac_imad": (nb * W_PER_BATCH_SIG / (bms * 1e-3)) / peak_w if L == 8 else None,
                     "exchange": "one all_gather of 192 B per rank" if world > 1 else "none (1 GPU)"}
-    if rank == 0 and verdict != 0:
-        raise SystemExit("batch verification of valid signatures returned verdict %r" % verdict)
+    if rank == 0 and (verdict != 0 or verdict_bad != 2):
+        raise SystemExit("batch verification returned verdicts %r / %r (expected 0 / 2)" % (verdict, verdict_bad))
     return out
 
 
