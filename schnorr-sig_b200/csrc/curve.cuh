@@ -292,7 +292,23 @@ SB_DEV void bucket_aggregate(const jac_pt* B, jac_pt* out) {
         jac_add_mem(out, &running, false);
     }
 }
-// returns [q]P == O (AffinePoint::is_torsion_free, src/signature.rs:182) and writes h*P
+// out = sum_{k=0..7} (2k+1) * B[k]  =  2 * sum k B[k] + sum B[k]      (13 additions + 1 doubling)
+SB_DEV void bucket_aggregate_odd(const jac_pt* B, jac_pt* out) {
+    jac_pt running = B[7];
+    *out = B[7];
+#pragma unroll 1
+    for (int k = 6; k >= 1; k--) {
+        jac_add_mem(&running, &B[k], false);
+        jac_add_mem(out, &running, false);
+    }
+    jac_add_mem(&running, &B[0], false);
+    jac_dbl_mem(out);
+    jac_add_mem(out, &running, false);
+}
+// returns [q]P == O (AffinePoint::is_torsion_free, src/signature.rs:182) and writes h*P.
+// One doubling chain D_j = 2^j P, j = 0..255.  q is consumed in its constant width-5 NAF (44 non-zero
+// odd digits at arbitrary bit positions -> 8 buckets of odd multiples, warp-uniform control flow);
+// h in signed 4-bit windows at every fourth step (per-thread digits, uniform trip count).
 SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) {
     jac_pt Bq[8], Bh[8];
 #pragma unroll 1
@@ -304,24 +320,18 @@ SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) 
     recode_signed_w4(h, hd);
     jac_pt D = P;
 #pragma unroll 1
-    for (int i = 0; i < 64; i++) {
-        SB_PHASE_SYNC(1);
-        if (i != 0) {
-#pragma unroll 1
-            for (int s = 0; s < 4; s++) {
-                SB_PHASE_SYNC(2);
-                jac_dbl_mem(&D);
-            }
+    for (int j = 0; j < 256; j++) {
+        if ((j & 3) == 0) SB_PHASE_SYNC(1);
+        if (j != 0) jac_dbl_mem(&D);
+        int dq = SB_QWNAF(j);
+        if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) >> 1], &D, dq < 0);  // warp-uniform
+        if ((j & 3) == 0) {
+            int dh = hd[j >> 2];
+            if (dh != 0) jac_add_mem(&Bh[(dh < 0 ? -dh : dh) - 1], &D, dh < 0);
         }
-        SB_PHASE_SYNC(2);
-        int dq = SB_QSW4(i);
-        if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) - 1], &D, dq < 0);  // warp-uniform
-        SB_PHASE_SYNC(2);
-        int dh = hd[i];
-        if (dh != 0) jac_add_mem(&Bh[(dh < 0 ? -dh : dh) - 1], &D, dh < 0);
     }
     jac_pt tq;
-    bucket_aggregate(Bq, &tq);
+    bucket_aggregate_odd(Bq, &tq);
     bucket_aggregate(Bh, hP);
     return jac_is_identity(tq);
 }
