@@ -26,8 +26,6 @@ using namespace sb;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-static constexpr int GTAB_WINDOWS = 32;
-static constexpr int GTAB_ENTRIES = 256;
 static constexpr size_t GTAB_U64 = (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 12;
 
 enum scratch_slot { SL_A = 0, SL_B, SL_C, SL_D, SL_E, SL_F, SL_G, SL_H, SL_I, SL_J, SL_K, SL_L, SL_COUNT };
@@ -323,13 +321,14 @@ __global__ void __launch_bounds__(128) k_compress(size_t n, const uint8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// fixed-base table of G:  gtab[i][b] = b * 256^i * G  (affine), i < 32, 1 <= b < 256
+// fixed-base table of G:  gtab[i][d] = d * 2^(13 i) * G  (affine), i < 20, 1 <= d <= 4096 (curve.cuh)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_gtab_bases(jac_pt* bases, fp6 gx, fp6 gy) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= GTAB_WINDOWS) return;
     jac_pt p = jac_from_affine(gx, gy, false);
-    for (int k = 0; k < 8 * i; k++) p = jac_dbl(p);
+#pragma unroll 1
+    for (int k = 0; k < GTAB_W * i; k++) jac_dbl_mem(&p);
     bases[i] = p;
 }
 __global__ void __launch_bounds__(128) k_gtab_fill(const jac_pt* __restrict__ bases, uint64_t* __restrict__ gtab) {
@@ -338,13 +337,14 @@ __global__ void __launch_bounds__(128) k_gtab_fill(const jac_pt* __restrict__ ba
     int i = t / GTAB_ENTRIES, b = t % GTAB_ENTRIES;
     jac_pt base = bases[i];
     jac_pt acc = jac_identity();
-    for (int bit = 7; bit >= 0; bit--) {
-        acc = jac_dbl(acc);
-        if ((b >> bit) & 1) acc = jac_add(acc, base);
+#pragma unroll 1
+    for (int bit = GTAB_W - 1; bit >= 0; bit--) {
+        jac_dbl_mem(&acc);
+        if ((b >> bit) & 1) jac_add_mem(&acc, &base, false);
     }
     fp6 x, y;
     bool inf;
-    jac_to_affine(acc, x, y, inf);
+    jac_to_affine(acc, x, y, inf);  // slot 0 (the identity) is written as zeros and never read
     uint64_t* o = gtab + (size_t)t * 12;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -473,8 +473,8 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     fp6 gx, gy;
     memcpy(gx.c, CHEETAH_GX, 48);
     memcpy(gy.c, CHEETAH_GY, 48);
-    k_gtab_bases<<<1, GTAB_WINDOWS, 0, ctx->stream>>>(bases, gx, gy);
-    k_gtab_fill<<<GTAB_WINDOWS * GTAB_ENTRIES / 128, 128, 0, ctx->stream>>>(bases, ctx->gtab);
+    k_gtab_bases<<<1, 32, 0, ctx->stream>>>(bases, gx, gy);
+    k_gtab_fill<<<(GTAB_WINDOWS * GTAB_ENTRIES + 127) / 128, 128, 0, ctx->stream>>>(bases, ctx->gtab);
     ctx->launches += 2;
     CREATE_TRY(cudaGetLastError());
     CREATE_TRY(cudaStreamSynchronize(ctx->stream));

@@ -69,21 +69,21 @@ API void hs_recode_odd_w4(const uint8_t* k, int8_t* digits64) {
 static std::vector<uint64_t> g_gtab;
 static void build_gtab() {
     if (!g_gtab.empty()) return;
-    g_gtab.assign((size_t)32 * 256 * 12, 0);
+    g_gtab.assign((size_t)GTAB_WINDOWS * GTAB_ENTRIES * 12, 0);
     fp6 gx = ld6(CHEETAH_GX), gy = ld6(CHEETAH_GY);
     jac_pt base = jac_from_affine(gx, gy, false);
-    for (int i = 0; i < 32; i++) {
+    for (int i = 0; i < GTAB_WINDOWS; i++) {
         jac_pt acc = jac_identity();
-        for (int b = 1; b < 256; b++) {
+        for (int b = 1; b < GTAB_ENTRIES; b++) {
             acc = jac_add(acc, base);
             fp6 x, y;
             bool inf;
             jac_to_affine(acc, x, y, inf);
-            uint64_t* o = &g_gtab[((size_t)i * 256 + b) * 12];
+            uint64_t* o = &g_gtab[((size_t)i * GTAB_ENTRIES + b) * 12];
             memcpy(o, x.c, 48);
             memcpy(o + 6, y.c, 48);
         }
-        for (int k = 0; k < 8; k++) base = jac_dbl(base);
+        for (int k = 0; k < GTAB_W; k++) base = jac_dbl(base);
     }
 }
 API const uint64_t* hs_gtab() {
