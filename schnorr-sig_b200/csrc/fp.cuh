@@ -305,6 +305,32 @@ SB_DEV fp_t fp_mul_small(fp_t a, uint32_t k) {
     return fp_reduce96((uint32_t)s, (uint32_t)(s >> 32), x2);
 }
 SB_DEV fp_t fp_mul7(fp_t a) { return fp_mul_small(a, 7); }
+// 7a as ANY 64-bit representative (not canonical): only ever fed to wide_mac as a multiplicand
+SB_DEV fp_t fp_mul7_nc(fp_t a) {
+#if defined(__CUDA_ARCH__)
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), t0, t1;
+    asm("{\n\t"
+        ".reg .u32 x1, x2, m0, m1, c;\n\t"
+        "mul.lo.u32 %0, %2, 7;\n\t"
+        "mul.hi.u32 x1, %2, 7;\n\t"
+        "mad.lo.cc.u32 %1, %3, 7, x1;\n\t"
+        "madc.hi.u32 x2, %3, 7, 0;\n\t"
+        "sub.cc.u32 m0, 0, x2;\n\t"       // + x2 * (2^32 - 1)
+        "subc.u32 m1, x2, 0;\n\t"
+        "add.cc.u32 %0, %0, m0;\n\t"
+        "addc.cc.u32 %1, %1, m1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.u32 c, 0, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(t0), "=&r"(t1)
+        : "r"(a0), "r"(a1));
+    return ((uint64_t)t1 << 32) | t0;
+#else
+    return fp_mul_small(a, 7);
+#endif
+}
 
 // a^(2^n)
 SB_DEV fp_t fp_sqr_n_nc(fp_t a, int n) {

@@ -58,7 +58,7 @@ SB_DEV bool fp6_is_canonical(const fp6& a) {
 SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
     fp_t b7[6];
 #pragma unroll
-    for (int j = 1; j < 6; j++) b7[j] = fp_mul7(b.c[j]);
+    for (int j = 1; j < 6; j++) b7[j] = fp_mul7_nc(b.c[j]);
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         wide_acc w;
@@ -75,7 +75,7 @@ SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
 SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) {
     fp_t a7[6];
 #pragma unroll
-    for (int j = 3; j < 6; j++) a7[j] = fp_mul7(a.c[j]);
+    for (int j = 3; j < 6; j++) a7[j] = fp_mul7_nc(a.c[j]);
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         wide_acc w;
@@ -141,7 +141,7 @@ struct fp3 {
 // out of line (by value, register ABI): the square-root / inversion code stays compact
 SB_DEV_NOINLINE fp3 fp3_mul(fp3 a, fp3 b) {
     fp3 r;
-    fp_t b7_1 = fp_mul7(b.c[1]), b7_2 = fp_mul7(b.c[2]);
+    fp_t b7_1 = fp_mul7_nc(b.c[1]), b7_2 = fp_mul7_nc(b.c[2]);
     wide_acc w;
     wide_zero(w);
     wide_mac(w, a.c[0], b.c[0]);
