@@ -41,6 +41,28 @@ W_PER_VERIFY_L8 = 787338          # SURVEY.md §8(d) canonical cost model v1, 8-
 W_PER_HASH_L8 = 56280
 W_PER_BATCH_SIG = 163900
 HBM_BYTES_PER_VERIFY = 177 + 8 + 8 + 1   # 81 sig + 96 key + msg + offset + verdict
+W_PER_PERMUTATION = 28140
+W_VERIFY_WITHOUT_HASH = W_PER_VERIFY_L8 - 2 * W_PER_PERMUTATION
+
+
+def permutations_for(msg_len):
+    """Rescue permutations of hash_message: 13 fixed elements + ceil(L/7) message elements, rate 8;
+    a partial last block costs one more permutation (padding), a full one does not."""
+    elems = 13 + -(-msg_len // 7)
+    return -(-elems // 8)
+
+
+def w_per_verify(msg_len):
+    return W_VERIFY_WITHOUT_HASH + permutations_for(msg_len) * W_PER_PERMUTATION
+
+
+def w_per_hash(msg_len):
+    return permutations_for(msg_len) * W_PER_PERMUTATION
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_verify launch from the ncu --set full capture
+# committed under profiles/ (per launch, keyed by log2 n); None where no capture exists
+TRAFFIC_BYTES_PER_LAUNCH = {}
 
 
 def parse_args():
@@ -306,7 +328,7 @@ def main():
     # ---- roofline of the dominant kernel (k_verify) ---------------------------------------------
     peak_w, peak_ms = eng.imad_peak(1 << 15)
     k_ms = float(np.mean(kernel_ms))
-    achieved_w = n * W_PER_VERIFY_L8 / (k_ms * 1e-3) if L == 8 else None
+    achieved_w = n * w_per_verify(L) / (k_ms * 1e-3)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -316,11 +338,11 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_achieved = n * (HBM_BYTES_PER_VERIFY - 8 + L) / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "imad", "achieved": (achieved_w or 0) / 1e12, "peak": peak_w / 1e12, "unit": "Tmul32x32/s",
-                "frac": (achieved_w / peak_w) if achieved_w else None, "traffic": None,
+                "frac": achieved_w / peak_w, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.log2n),
                 "kernel": "k_verify", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / dev_ms,
                 "peak_source": "measured live: schnorr_b200_imad_peak (K6, IMAD.WIDE.U32 chains, full grid)",
                 "peak_nominal": 148 * 32 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12 if True else None,
-                "algorithmic_units": "%d wide multiplies per verification (SURVEY.md 8d cost model v1) x %d per launch" % (W_PER_VERIFY_L8, n),
+                "algorithmic_units": "%d wide multiplies per verification (SURVEY.md 8d cost model v1, %d-byte message) x %d per launch" % (w_per_verify(L), L, n),
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
 
@@ -375,7 +397,7 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
     hms = a.elapsed_time(b)
     peak_w, _ = eng.imad_peak(1 << 15)
     out["hash"] = {"metric": "rescue_hash_message_per_sec", "value": world * n / (hms * 1e-3), "n_per_gpu": n, "msg_len": L,
-                   "ms": hms, "roofline_frac_imad": (n * W_PER_HASH_L8 / (hms * 1e-3)) / peak_w if L == 8 else None}
+                   "ms": hms, "roofline_frac_imad": (n * w_per_hash(L) / (hms * 1e-3)) / peak_w}
     # K3/K4: one batch of nb signatures per GPU, partial MSM per rank + one small gather + finish on rank 0
     import schnorr_sig_b200 as sb
     blog = args.batch_log2n if args.batch_log2n is not None else (16 if world == 1 else 21)
@@ -434,7 +456,7 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
     out["batch"] = {"metric": "schnorr_batch_verified_signatures_per_sec", "value": world * nb / (bms * 1e-3),
                     "signatures_per_gpu": nb, "ms": bms, "verdict": verdict,
                     "verdict_with_one_corrupted_signature_on_last_rank": verdict_bad,
-                    "roofline_frac_imad": (nb * W_PER_BATCH_SIG / (bms * 1e-3)) / peak_w if L == 8 else None,
+                    "roofline_frac_imad": (nb * (W_PER_BATCH_SIG + (permutations_for(L) - 2) * W_PER_PERMUTATION) / (bms * 1e-3)) / peak_w,
                     "exchange": "one all_gather of 192 B per rank" if world > 1 else "none (1 GPU)"}
     if rank == 0 and (verdict != 0 or verdict_bad != 2):
         raise SystemExit("batch verification returned verdicts %r / %r (expected 0 / 2)" % (verdict, verdict_bad))
