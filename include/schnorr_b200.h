@@ -78,6 +78,14 @@ int schnorr_b200_verify_many_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t 
                                  const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
                                  uint8_t *verdicts);
 
+/* KeyedSignature::from_bytes + KeyedSignature::verify over n 130-byte wire records
+ * (49-byte compressed public key || 81-byte signature)   src/signature.rs:232-271, src/constants.rs:33
+ * The key is decompressed on the device; a record whose key does not decode gets verdict 3. */
+int schnorr_b200_verify_keyed_many(schnorr_b200_ctx *ctx, size_t n, const uint8_t *keyed130, const uint8_t *msgs,
+                                   const uint64_t *msg_off, uint8_t *verdicts);
+int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *keyed130, const uint8_t *msgs,
+                                       const uint64_t *msg_off, uint8_t *verdicts);
+
 /* verify_batch(&[Signature], &[PublicKey], &[&[u8]], rng)                  src/batch.rs:31-50
  * = generate_batch_coefficients (:56-81) + verify_prepared_batch (:84-130).
  * rand32: n x 32 B caller-supplied randomisers s_i (reduced mod q) -- the seam the reference has at

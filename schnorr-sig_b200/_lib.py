@@ -22,6 +22,8 @@ _SIGNATURES = {
     "schnorr_b200_hash_messages_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 5),
     "schnorr_b200_verify_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6),
     "schnorr_b200_verify_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6),
+    "schnorr_b200_verify_keyed_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
+    "schnorr_b200_verify_keyed_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
     "schnorr_b200_verify_batch": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6 + [C.POINTER(C.c_int), _u8p, _u8p]),
     "schnorr_b200_batch_partial_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
     "schnorr_b200_batch_finish_dev": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p]),

@@ -276,6 +276,29 @@ def verify_batch(signatures, public_keys, messages, rng=None) -> Result:
     return verify_prepared_batch(rand, signatures, public_keys, messages)
 
 
+def locate_invalid(signatures, public_keys, messages):
+    """Failed-batch localisation (the reference returns one Err for the whole batch,
+    src/batch.rs:125-129): re-checks the items one by one on the GPU (the independent-verification kernel)
+    and returns [(index, SignatureError), ...].  Note the single-verification semantics apply here:
+    an off-subgroup key is reported as InvalidPublicKey although verify_batch itself does not test it."""
+    n = len(signatures)
+    assert len(public_keys) == n and len(messages) == n
+    if n == 0:
+        return []
+    sigs = np.frombuffer(b"".join(s.to_bytes() for s in signatures), dtype=np.uint8).reshape(n, 81)
+    pks = np.frombuffer(b"".join(k.xy for k in public_keys), dtype=np.uint8).reshape(n, 96)
+    inf = np.array([k.infinity for k in public_keys], dtype=np.uint8)
+    blob, off = _pack(messages)
+    v = default_engine().verify_many(sigs, pks, inf, blob, off)
+    out = []
+    for i in np.nonzero(v)[0]:
+        if v[i] == MALFORMED:
+            raise PanicError("signature %d has a non-canonical encoding" % i)
+        out.append((int(i), SignatureError(SignatureError.InvalidPublicKey if v[i] == INVALID_PUBLIC_KEY
+                                           else SignatureError.InvalidSignature)))
+    return out
+
+
 def verify_prepared_batch(randomizers32, signatures, public_keys, messages) -> Result:
     """The reference's seam for caller-supplied randomisers (src/batch.rs:84-130)."""
     n = len(signatures)

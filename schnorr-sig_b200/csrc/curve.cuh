@@ -262,9 +262,23 @@ SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab)
 #if defined(__CUDACC__)
 __constant__ int8_t c_q_sw4[64];  // CHEETAH_Q_SW4, filled at context creation
 #define SB_QSW4(i) c_q_sw4[i]
+__constant__ int8_t c_q_wnaf4[256];  // CHEETAH_Q_WNAF4
 #else
 #define SB_QSW4(i) CHEETAH_Q_SW4[i]
 #endif
+// width of the NAF used for q in the subgroup check: 5 -> 8 buckets (44 + 14 additions),
+// 4 -> 4 buckets (53 + 6 additions, 576 B less local memory per thread)
+#ifndef SB_Q_NAF_W
+#define SB_Q_NAF_W 5  // measured: width 5 = 7.84 M/s, width 4 = 7.74 M/s (profiles/r1_variants.md)
+#endif
+#if SB_Q_NAF_W == 5
+#define SB_QNAF(i) SB_QWNAF(i)
+#elif defined(__CUDACC__)
+#define SB_QNAF(i) c_q_wnaf4[i]
+#else
+#define SB_QNAF(i) CHEETAH_Q_WNAF4[i]
+#endif
+static constexpr int SB_Q_BUCKETS = 1 << (SB_Q_NAF_W - 2);
 
 // Keeping the warps of a block in the same phase of the loop lets them share instruction-cache lines
 // (the point routines are ~4k instructions, larger than the cache): a block barrier per point
@@ -298,12 +312,12 @@ SB_DEV void bucket_aggregate(const jac_pt* B, jac_pt* out) {
         jac_add_mem(out, &running, false);
     }
 }
-// out = sum_{k=0..7} (2k+1) * B[k]  =  2 * sum k B[k] + sum B[k]      (13 additions + 1 doubling)
-SB_DEV void bucket_aggregate_odd(const jac_pt* B, jac_pt* out) {
-    jac_pt running = B[7];
-    *out = B[7];
+// out = sum_{k<nb} (2k+1) * B[k]  =  2 * sum k B[k] + sum B[k]      (2 nb - 3 additions + 1 doubling)
+SB_DEV void bucket_aggregate_odd(const jac_pt* B, int nb, jac_pt* out) {
+    jac_pt running = B[nb - 1];
+    *out = B[nb - 1];
 #pragma unroll 1
-    for (int k = 6; k >= 1; k--) {
+    for (int k = nb - 2; k >= 1; k--) {
         jac_add_mem(&running, &B[k], false);
         jac_add_mem(out, &running, false);
     }
@@ -312,16 +326,15 @@ SB_DEV void bucket_aggregate_odd(const jac_pt* B, jac_pt* out) {
     jac_add_mem(out, &running, false);
 }
 // returns [q]P == O (AffinePoint::is_torsion_free, src/signature.rs:182) and writes h*P.
-// One doubling chain D_j = 2^j P, j = 0..255.  q is consumed in its constant width-5 NAF (44 non-zero
-// odd digits at arbitrary bit positions -> 8 buckets of odd multiples, warp-uniform control flow);
+// One doubling chain D_j = 2^j P, j = 0..255.  q is consumed in its constant width-w NAF (non-zero odd
+// digits at arbitrary bit positions -> 2^(w-2) buckets of odd multiples, warp-uniform control flow);
 // h in signed 4-bit windows at every fourth step (per-thread digits, uniform trip count).
 SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) {
-    jac_pt Bq[8], Bh[8];
+    jac_pt Bq[SB_Q_BUCKETS], Bh[8];
 #pragma unroll 1
-    for (int b = 0; b < 8; b++) {
-        Bq[b] = jac_identity();
-        Bh[b] = jac_identity();
-    }
+    for (int b = 0; b < 8; b++) Bh[b] = jac_identity();
+#pragma unroll 1
+    for (int b = 0; b < SB_Q_BUCKETS; b++) Bq[b] = jac_identity();
     int8_t hd[64];
     recode_signed_w4(h, hd);
     jac_pt D = P;
@@ -329,7 +342,7 @@ SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) 
     for (int j = 0; j < 256; j++) {
         if ((j & 3) == 0) SB_PHASE_SYNC(1);
         if (j != 0) jac_dbl_mem(&D);
-        int dq = SB_QWNAF(j);
+        int dq = SB_QNAF(j);
         if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) >> 1], &D, dq < 0);  // warp-uniform
         if ((j & 3) == 0) {
             int dh = hd[j >> 2];
@@ -337,7 +350,7 @@ SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) 
         }
     }
     jac_pt tq;
-    bucket_aggregate_odd(Bq, &tq);
+    bucket_aggregate_odd(Bq, SB_Q_BUCKETS, &tq);
     bucket_aggregate(Bh, hP);
     return jac_is_identity(tq);
 }

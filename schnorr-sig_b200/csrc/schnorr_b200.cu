@@ -320,6 +320,31 @@ __global__ void __launch_bounds__(128) k_compress(size_t n, const uint8_t* __res
     o[48] = compress_flags(y, inf);
 }
 
+// KeyedSignature wire records (src/signature.rs:237-271): 49-byte compressed public key || 81-byte
+// signature.  The key is decompressed on the device; records whose key does not decode get verdict 3
+// (KeyedSignature::from_bytes returns None for them).
+__global__ void __launch_bounds__(128) k_split_keyed(size_t n, const uint8_t* __restrict__ keyed130, uint8_t* __restrict__ pk96,
+                                                     uint8_t* __restrict__ pk_inf, uint8_t* __restrict__ ok,
+                                                     uint8_t* __restrict__ sigs81) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* rec = keyed130 + 130 * i;
+    fp6 x;
+#pragma unroll
+    for (int k = 0; k < 6; k++) x.c[k] = load_u64_le(rec + 8 * k);
+    fp6 ox, oy;
+    bool inf;
+    bool good = decompress_point(x, rec[48], ox, oy, inf);
+    store_point96(pk96 + 96 * i, ox, oy);
+    pk_inf[i] = inf ? 1 : 0;
+    ok[i] = good ? 1 : 0;
+    for (int k = 0; k < 81; k++) sigs81[81 * i + k] = rec[49 + k];
+}
+__global__ void k_mask_verdicts(size_t n, const uint8_t* __restrict__ ok, uint8_t* __restrict__ verdicts) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !ok[i]) verdicts[i] = VERDICT_MALFORMED;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fixed-base table of G:  gtab[i][d] = d * 2^(13 i) * G  (affine), i < 20, 1 <= d <= 4096 (curve.cuh)
 // ------------------------------------------------------------------------------------------------
@@ -467,6 +492,7 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     CREATE_TRY(cudaMemcpyToSymbol(c_ark, RESCUE_ARK, sizeof(uint64_t) * 2 * RESCUE_ROUNDS * 12));
     CREATE_TRY(cudaMemcpyToSymbol(c_q_wnaf5, CHEETAH_Q_WNAF5, 256));
     CREATE_TRY(cudaMemcpyToSymbol(c_q_sw4, CHEETAH_Q_SW4, 64));
+    CREATE_TRY(cudaMemcpyToSymbol(c_q_wnaf4, CHEETAH_Q_WNAF4, 256));
     CREATE_TRY(cudaMalloc(&ctx->gtab, GTAB_U64 * sizeof(uint64_t)));
     jac_pt* bases = nullptr;
     CREATE_TRY(cudaMalloc(&bases, sizeof(jac_pt) * GTAB_WINDOWS));
@@ -587,6 +613,46 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
     if (int rc = ensure_scratch(ctx, SL_H, n, &d_out)) return rc;
     if (int rc = schnorr_b200_verify_many_dev(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
                                               (uint64_t*)d_off, (uint8_t*)d_out))
+        return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- KeyedSignature::verify over wire records -------------------------------------------------
+int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,
+                                       const uint64_t* msg_off, uint8_t* verdicts) {
+    if (!ctx || (n && (!keyed130 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_pk, *d_inf, *d_ok, *d_sig;
+    if (int rc = ensure_scratch(ctx, SL_J, n * 96, &d_pk)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_K, n * 2, &d_inf)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_L, n * 81 + 256, &d_sig)) return rc;
+    d_ok = (uint8_t*)d_inf + n;
+    k_split_keyed<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, keyed130, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_ok,
+                                                           (uint8_t*)d_sig);
+    ctx->launches += 1;
+    if (int rc = schnorr_b200_verify_many_dev(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, msgs, msg_off, verdicts))
+        return rc;
+    k_mask_verdicts<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, (uint8_t*)d_ok, verdicts);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,
+                                   const uint64_t* msg_off, uint8_t* verdicts) {
+    if (!ctx || (n && (!keyed130 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    void *d_rec, *d_m, *d_off, *d_out;
+    if (int rc = stage_in(ctx, SL_D, keyed130, n * 130, &d_rec)) return rc;
+    if (int rc = stage_in(ctx, SL_F, msgs, mb, &d_m)) return rc;
+    if (int rc = stage_in(ctx, SL_G, msg_off, (n + 1) * 8, &d_off)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n, &d_out)) return rc;
+    if (int rc = schnorr_b200_verify_keyed_many_dev(ctx, n, (uint8_t*)d_rec, (uint8_t*)d_m, (uint64_t*)d_off, (uint8_t*)d_out))
         return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

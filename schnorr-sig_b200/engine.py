@@ -116,6 +116,17 @@ class Engine:
                                                      _ptr(off), _ptr(out)), "verify_many")
         return out
 
+    def verify_keyed_many(self, keyed130, msgs, off):
+        """KeyedSignature wire records (49-byte compressed key || 81-byte signature) -> verdicts."""
+        keyed130, msgs = _u8(keyed130, 130), _u8(msgs)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = keyed130.shape[0]
+        self._check_offsets(n, n, off, msgs)
+        out = np.full(n, 255, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_verify_keyed_many(self._h, n, _ptr(keyed130), _ptr(msgs), _ptr(off), _ptr(out)),
+                    "verify_keyed_many")
+        return out
+
     def verify_batch(self, sigs81, pk96, pk_inf, msgs, off, rand32):
         """-> (verdict, lhs97, rhs97)"""
         sigs81, pk96, msgs, rand32 = _u8(sigs81, 81), _u8(pk96, 96), _u8(msgs), _u8(rand32, 32)

@@ -63,3 +63,29 @@ def test_cpp_facade_example_runs():
         g.build()
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+def test_keyed_signature_wire_records_and_localisation():
+    """f2: 130-byte KeyedSignature records verified straight from the wire (key decompressed on device);
+    f3: failed-batch localisation."""
+    import schnorr_sig_b200 as s
+    eng = s.default_engine(0)
+    w = make_workload(8, 50, lens=[int(x) for x in np.random.default_rng(8).integers(0, 60, 50)])
+    comp = np.stack([cref.compress(w["pk"][i]) for i in range(50)])
+    keyed = np.concatenate([comp, w["sigs"]], axis=1)
+    assert keyed.shape == (50, 130)
+    assert (eng.verify_keyed_many(keyed, w["blob"], w["off"]) == 0).all()
+    bad = keyed.copy()
+    bad[3, 48] = 0xFF            # undecodable key -> 3
+    bad[4, 49 + 49:] = 0         # e := 0 -> 2
+    bad[5, 48] ^= 0x40           # other root: -P, a different (valid) key -> 2
+    got = eng.verify_keyed_many(bad, w["blob"], w["off"])
+    assert list(got[3:6]) == [3, 2, 2] and (np.delete(got, [3, 4, 5]) == 0).all()
+    # localisation through the facade
+    sigs = [s.Signature(bytes(x[:49]), bytes(x[49:])) for x in w["sigs"]]
+    pks = [s.PublicKey(bytes(k)) for k in w["pk"]]
+    assert s.verify_batch(sigs, pks, w["msgs"]).is_ok() and s.locate_invalid(sigs, pks, w["msgs"]) == []
+    pks[7], pks[9] = pks[9], pks[7]
+    assert s.verify_batch(sigs, pks, w["msgs"]).is_err()
+    loc = s.locate_invalid(sigs, pks, w["msgs"])
+    assert [i for i, _ in loc] == [7, 9] and all(e == s.SignatureError(s.SignatureError.InvalidSignature) for _, e in loc)

@@ -73,6 +73,8 @@ def main():
 
     q_wnaf5 = wnaf(Q, 5)
     assert sum(d << i for i, d in enumerate(q_wnaf5)) == Q
+    q_wnaf4 = wnaf(Q, 4)
+    assert sum(d << i for i, d in enumerate(q_wnaf4)) == Q and len(q_wnaf4) == 256
     # signed fixed 4-bit windows of q: q = sum d_i 16^i, d_i in [-8, 8] (shared-doubling subgroup check)
     q_sw4, k, carry = [], Q, 0
     for _ in range(64):
@@ -156,6 +158,8 @@ def main():
     h.append("/* width-5 NAF of q, least-significant digit first (uniform addition chain of the subgroup check) */\n")
     h.append("#define CHEETAH_Q_WNAF5_LEN %d\n" % len(q_wnaf5))
     h.append(arr8("CHEETAH_Q_WNAF5", q_wnaf5))
+    h.append("/* width-4 NAF of q (digits +-1,3,5,7), least-significant digit first */\n")
+    h.append(arr8("CHEETAH_Q_WNAF4", q_wnaf4))
     h.append("/* signed 4-bit windows of q, least-significant first: q = sum d_i 16^i, |d_i| <= 8 */\n")
     h.append(arr8("CHEETAH_Q_SW4", q_sw4))
     h.append("/* Frobenius: (u^i)^p = FP6_FROB[i] * u^i */\n")
