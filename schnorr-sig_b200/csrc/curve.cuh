@@ -11,8 +11,7 @@
 //
 // Code-size discipline: the hot loops call ONE out-of-line copy each of jac_dbl_mem / jac_add_mem /
 // jac_madd_mem (operating on points held in thread-local memory), which in turn call one copy of
-// fp6_mul / fp6_sqr.  The whole scalar-multiplication loop then fits the instruction cache and the
-// accumulator does not pin 36 registers across calls.
+// fp6_mul / fp6_sqr: small instruction-cache footprint, and no point pins 36 registers across calls.
 #pragma once
 #include "fp6.cuh"
 #include "scalar.cuh"
@@ -30,7 +29,6 @@ SB_DEV jac_pt jac_from_affine(const fp6& x, const fp6& y, bool inf) {
     if (inf) r = jac_identity();
     return r;
 }
-SB_DEV jac_pt jac_neg(const jac_pt& p) { return jac_pt{p.X, fp6_neg(p.Y), p.Z}; }
 
 // dbl-2007-bl with a = 1: 1M + 8S.  Complete: Z = 0 or Y = 0 (order-2 point) both give Z3 = 0.
 SB_DEV jac_pt jac_dbl(const jac_pt& p) {
@@ -140,65 +138,12 @@ SB_DEV bool jac_x_equals(const jac_pt& p, const fp6& x) {
     return fp6_eq(p.X, fp6_mul(x, fp6_sqr(p.Z)));
 }
 
-// ---------------------------------------------------------------------------------------------
-// Odd-multiples table of a variable base:  T[k] = (2k+1) * P,  k = 0..7  (1 dbl + 7 add).
-// Shared by the subgroup check (width-5 NAF of the constant q) and by the regular signed-odd
-// window-4 recoding of the challenge scalar.
-SB_DEV void build_odd_table(jac_pt* T, const jac_pt& P) {
-    jac_pt P2 = P;
-    jac_dbl_mem(&P2);
-    T[0] = P;
-#pragma unroll 1
-    for (int k = 1; k < 8; k++) {
-        T[k] = T[k - 1];
-        jac_add_mem(&T[k], &P2, false);
-    }
-}
-
 #if defined(__CUDACC__)
 __constant__ int8_t c_q_wnaf5[256];  // CHEETAH_Q_WNAF5, filled at context creation
 #define SB_QWNAF(i) c_q_wnaf5[i]
 #else
 #define SB_QWNAF(i) CHEETAH_Q_WNAF5[i]
 #endif
-
-// AffinePoint::is_torsion_free (call site src/signature.rs:182): [q]P == O, evaluated along the
-// fixed width-5 NAF addition chain of q (uniform across the warp: digits are constants).
-SB_DEV bool torsion_free_with_table(const jac_pt* T) {
-    int top = 255;
-    while (SB_QWNAF(top) == 0) top--;
-    int d = SB_QWNAF(top);  // positive by construction
-    jac_pt acc = T[d >> 1];
-#pragma unroll 1
-    for (int i = top - 1; i >= 0; i--) {
-        jac_dbl_mem(&acc);
-        int di = SB_QWNAF(i);
-        if (di != 0) {  // warp-uniform branch
-            int idx = (di < 0 ? -di : di) >> 1;
-            jac_add_mem(&acc, &T[idx], di < 0);
-        }
-    }
-    return jac_is_identity(acc);
-}
-
-// Regular signed-odd recoding, window 4 (Joye-Tunstall): an ODD k < 2^255 becomes 64 odd digits
-// d_i in {+-1, +-3, ..., +-15} with k = sum d_i 16^i:  d_i = (k mod 32) - 16, k <- (k - d_i) / 16.
-// Digits are returned packed: bit 4 = sign, bits 0..2 = table index (|d|-1)/2.
-SB_DEV void recode_odd_w4(const scalar& k, uint8_t* digits /*64*/) {
-    scalar v = k;
-#pragma unroll 1
-    for (int i = 0; i < 63; i++) {
-        int d = (int)(v.l[0] & 31) - 16;  // odd, in [-15, 15]
-        // v - d has low five bits 10000b; dividing by 16 leaves an odd value again
-        v.l[0] = (v.l[0] & ~31u) | 16u;
-#pragma unroll
-        for (int j = 0; j < 7; j++) v.l[j] = (v.l[j] >> 4) | (v.l[j + 1] << 28);
-        v.l[7] >>= 4;
-        int a = d < 0 ? -d : d;
-        digits[i] = (uint8_t)(((d < 0) ? 16 : 0) | (a >> 1));
-    }
-    digits[63] = (uint8_t)((v.l[0] & 31) >> 1);  // remaining value: odd and <= 9 for k < 2^255
-}
 
 // Fixed-base table of G (the reference's BASEPOINT_TABLE): signed 13-bit windows,
 //   gtab[i][d] = d * 2^(13 i) * G   (affine x || y, 12 x u64),  i < 20,  1 <= d <= 4096  (slot 0 unused)
@@ -221,31 +166,6 @@ SB_DEV void fixed_base_accumulate(jac_pt* acc, const scalar& k, const uint64_t* 
     }
 }
 
-// h*P + e*G with the odd table of P and the fixed-base table of G; h, e canonical scalars.
-// (multiply_double_with_basepoint_vartime, src/signature.rs:196-198.)
-SB_DEV jac_pt double_base_mul(const jac_pt* T, const scalar& h, const scalar& e, const uint64_t* __restrict__ gtab) {
-    // make the variable-base scalar odd: for even h use q - h (odd) and flip every digit's sign;
-    // h = 0 uses k = q itself ([q]P = O for a key that passed the subgroup check).
-    bool flip = (h.l[0] & 1) == 0;
-    scalar k = flip ? sc_neg(h) : h;
-    if (sc_is_zero(h)) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) k.l[i] = SB_CONST_Q(i);
-    }
-    uint8_t dg[64];
-    recode_odd_w4(k, dg);
-    jac_pt acc = T[dg[63] & 7];
-    if (((dg[63] >> 4) & 1) != (flip ? 1 : 0)) acc.Y = fp6_neg(acc.Y);
-#pragma unroll 1
-    for (int i = 62; i >= 0; i--) {
-#pragma unroll 1
-        for (int s = 0; s < 4; s++) jac_dbl_mem(&acc);
-        jac_add_mem(&acc, &T[dg[i] & 7], ((dg[i] >> 4) & 1) != (flip ? 1 : 0));
-    }
-    fixed_base_accumulate(&acc, e, gtab);
-    return acc;
-}
-
 // k*G (BASEPOINT_TABLE * scalar: src/public.rs:29, src/signature.rs:67,116, src/batch.rs:98-100)
 SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab) {
     jac_pt acc = jac_identity();
@@ -260,11 +180,7 @@ SB_DEV jac_pt fixed_base_mul(const scalar& k, const uint64_t* __restrict__ gtab)
 //     B[|d_i|] += sign(d_i) * D_i        then        k*P = sum_{m=1..8} m * B[m]   (14 additions)
 // q's digits are constants (warp-uniform additions); h's digits are per thread.
 #if defined(__CUDACC__)
-__constant__ int8_t c_q_sw4[64];  // CHEETAH_Q_SW4, filled at context creation
-#define SB_QSW4(i) c_q_sw4[i]
-__constant__ int8_t c_q_wnaf4[256];  // CHEETAH_Q_WNAF4
-#else
-#define SB_QSW4(i) CHEETAH_Q_SW4[i]
+__constant__ int8_t c_q_wnaf4[256];  // CHEETAH_Q_WNAF4, filled at context creation
 #endif
 // width of the NAF used for q in the subgroup check: 5 -> 8 buckets (44 + 14 additions),
 // 4 -> 4 buckets (53 + 6 additions, 576 B less local memory per thread)

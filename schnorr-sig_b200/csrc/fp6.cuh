@@ -41,12 +41,6 @@ SB_DEV bool fp6_eq(const fp6& a, const fp6& b) {
     for (int i = 0; i < 6; i++) d |= a.c[i] ^ b.c[i];
     return d == 0;
 }
-SB_DEV fp6 fp6_select(bool pick_b, const fp6& a, const fp6& b) {
-    fp6 r;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.c[i] = pick_b ? b.c[i] : a.c[i];
-    return r;
-}
 // every limb canonical?  (Fp6::from_bytes is None otherwise -> the reference panics, src/signature.rs:186)
 SB_DEV bool fp6_is_canonical(const fp6& a) {
     bool ok = true;
@@ -126,13 +120,6 @@ SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
     return r;
 }
 #endif
-
-SB_DEV fp6 fp6_mul_small(const fp6& a, uint32_t k) {
-    fp6 r;
-#pragma unroll
-    for (int i = 0; i < 6; i++) r.c[i] = fp_mul_small(a.c[i], k);
-    return r;
-}
 
 // ---- cubic subfield Fp3 = Fp[v]/(v^3 - 7), v = u^2, used by inversion and square roots ----
 struct fp3 {

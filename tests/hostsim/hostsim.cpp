@@ -56,16 +56,6 @@ API void hs_sc_add(const uint8_t* a, const uint8_t* b, uint8_t* r) { stsc(r, sc_
 API void hs_sc_sub(const uint8_t* a, const uint8_t* b, uint8_t* r) { stsc(r, sc_sub(ldsc(a), ldsc(b))); }
 API void hs_sc_from_u256(const uint8_t* a, uint8_t* r) { stsc(r, sc_from_u256(ldsc(a))); }
 API int hs_sc_geq_q(const uint8_t* a) { return sc_geq_q(ldsc(a)); }
-// recode an odd scalar and return sum d_i 16^i reassembled as 64 signed digits
-API void hs_recode_odd_w4(const uint8_t* k, int8_t* digits64) {
-    uint8_t dg[64];
-    recode_odd_w4(ldsc(k), dg);
-    for (int i = 0; i < 64; i++) {
-        int mag = 2 * (dg[i] & 7) + 1;
-        digits64[i] = (int8_t)((dg[i] >> 4) & 1 ? -mag : mag);
-    }
-}
-
 static std::vector<uint64_t> g_gtab;
 static void build_gtab() {
     if (!g_gtab.empty()) return;
@@ -132,15 +122,16 @@ API void hs_fixed_base_mul(const uint8_t* k32, uint8_t* out96, int* out_inf) {
     store_aff(fixed_base_mul(sc_from_u256(ldsc(k32)), g_gtab.data()), out96, out_inf);
 }
 API int hs_torsion_free(const uint8_t* p96, int inf) {
-    jac_pt T[8];
-    build_odd_table(T, load_pt(p96, inf));
-    return torsion_free_with_table(T);
+    jac_pt r;
+    return torsion_check_and_mul(load_pt(p96, inf), sc_zero(), &r);
 }
+// h*P + e*G exactly as verify_points composes it
 API void hs_double_base(const uint8_t* p96, int inf, const uint8_t* h32, const uint8_t* e32, uint8_t* out96, int* out_inf) {
     build_gtab();
-    jac_pt T[8];
-    build_odd_table(T, load_pt(p96, inf));
-    store_aff(double_base_mul(T, ldsc(h32), ldsc(e32), g_gtab.data()), out96, out_inf);
+    jac_pt r;
+    torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r);
+    fixed_base_accumulate(&r, ldsc(e32), g_gtab.data());
+    store_aff(r, out96, out_inf);
 }
 // shared-doubling core: returns the subgroup verdict and h*P
 API int hs_torsion_check_and_mul(const uint8_t* p96, int inf, const uint8_t* h32, uint8_t* out96, int* out_inf) {

@@ -115,16 +115,6 @@ def test_scalar_field(hostsim):
         assert bool(hostsim.hs_sc_geq_q(p(V))) == (v >= o.Q)
 
 
-def test_regular_recoding(hostsim):
-    rng = np.random.default_rng(7)
-    d = np.zeros(64, dtype=np.int8)
-    for k in [1, 3, 15, 17, o.Q, o.Q - 2, 2**255 - 1] + [int_le(s) | 1 for s in rand_scalars(rng, 50)]:
-        K = np.frombuffer(k.to_bytes(32, "little"), dtype=np.uint8).copy()
-        hostsim.hs_recode_odd_w4(p(K), p(d))
-        assert all(int(x) % 2 != 0 and abs(int(x)) <= 15 for x in d)
-        assert sum(int(x) << (4 * i) for i, x in enumerate(d)) == k
-
-
 def test_point_formulas(hostsim):
     rng = np.random.default_rng(8)
     G = o.generator()

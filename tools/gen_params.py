@@ -75,14 +75,6 @@ def main():
     assert sum(d << i for i, d in enumerate(q_wnaf5)) == Q
     q_wnaf4 = wnaf(Q, 4)
     assert sum(d << i for i, d in enumerate(q_wnaf4)) == Q and len(q_wnaf4) == 256
-    # signed fixed 4-bit windows of q: q = sum d_i 16^i, d_i in [-8, 8] (shared-doubling subgroup check)
-    q_sw4, k, carry = [], Q, 0
-    for _ in range(64):
-        raw = (k & 15) + carry
-        k >>= 4
-        carry = 1 if raw > 8 else 0
-        q_sw4.append(raw - 16 if raw > 8 else raw)
-    assert carry == 0 and k == 0 and sum(d << (4 * i) for i, d in enumerate(q_sw4)) == Q
 
     params = {
         "_about": "constants of the Cheetah/Rescue Schnorr path with provenance tags; see tools/gen_params.py",
@@ -160,8 +152,6 @@ def main():
     h.append(arr8("CHEETAH_Q_WNAF5", q_wnaf5))
     h.append("/* width-4 NAF of q (digits +-1,3,5,7), least-significant digit first */\n")
     h.append(arr8("CHEETAH_Q_WNAF4", q_wnaf4))
-    h.append("/* signed 4-bit windows of q, least-significant first: q = sum d_i 16^i, |d_i| <= 8 */\n")
-    h.append(arr8("CHEETAH_Q_SW4", q_sw4))
     h.append("/* Frobenius: (u^i)^p = FP6_FROB[i] * u^i */\n")
     h.append(arr64("FP6_FROB", frob6))
     h.append("/* Rescue circulant MDS first row [RECALLED] and full matrix */\n")
