@@ -40,6 +40,10 @@ struct schnorr_b200_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
+    size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
+    cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
+    static constexpr int MAX_CHUNKS = 16;
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
     std::string err;
 };
 
@@ -487,6 +491,14 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    {
+        int per_sm = 0;
+        CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verify, VERIFY_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+        ctx->verify_wave = (size_t)ctx->sm_count * per_sm * VERIFY_THREADS;
+    }
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int c = 0; c < schnorr_b200_ctx::MAX_CHUNKS; c++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&ctx->ev_k0));
     CREATE_TRY(cudaEventCreate(&ctx->ev_k1));
     CREATE_TRY(cudaMemcpyToSymbol(c_ark, RESCUE_ARK, sizeof(uint64_t) * 2 * RESCUE_ROUNDS * 12));
@@ -516,6 +528,9 @@ void schnorr_b200_destroy(schnorr_b200_ctx* ctx) {
     for (int s = 0; s < SL_COUNT; s++)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     if (ctx->gtab) cudaFree(ctx->gtab);
+    for (int c = 0; c < schnorr_b200_ctx::MAX_CHUNKS; c++)
+        if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -595,6 +610,9 @@ int schnorr_b200_verify_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t*
     return SCHNORR_B200_OK;
 }
 
+// Host entry point.  Large calls are pipelined: the batch is cut into up to 8 chunks; chunk c+1 is copied
+// host->device on a second stream while chunk c is being verified, and each chunk's verdicts are copied
+// back as soon as its kernel ends, so the PCIe time hides behind the kernels.
 int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
     if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
@@ -603,18 +621,55 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
     size_t mb = msg_off[n];
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_out;
-    if (int rc = stage_in(ctx, SL_D, sigs81, n * 81, &d_sig)) return rc;
-    if (int rc = stage_in(ctx, SL_E, pk96, n * 96, &d_pk)) return rc;
-    if (int rc = stage_in(ctx, SL_F, msgs, mb, &d_m)) return rc;
-    if (int rc = stage_in(ctx, SL_G, msg_off, (n + 1) * 8, &d_off)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_D, n * 81, &d_sig)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 96, &d_pk)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_F, mb, &d_m)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_G, (n + 1) * 8, &d_off)) return rc;
     if (pk_inf)
-        if (int rc = stage_in(ctx, SL_I, pk_inf, n, &d_inf)) return rc;
+        if (int rc = ensure_scratch(ctx, SL_I, n, &d_inf)) return rc;
     if (int rc = ensure_scratch(ctx, SL_H, n, &d_out)) return rc;
-    if (int rc = schnorr_b200_verify_many_dev(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
-                                              (uint64_t*)d_off, (uint8_t*)d_out))
-        return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    soa_batch soa;
+    if (int rc = alloc_soa(ctx, n, &soa)) return rc;
+    // chunk plan in whole kernel waves (no partial-wave tail between chunks): 1 wave, 2 waves, the rest.
+    // Copying is ~16x faster than verifying, so the copy of the rest hides behind the first three waves.
+    size_t bounds[4] = {0, n, n, n};
+    int chunks = 1;
+    if (n > 6 * ctx->verify_wave) {
+        bounds[1] = ctx->verify_wave;
+        bounds[2] = 3 * ctx->verify_wave;
+        bounds[3] = n;
+        chunks = 3;
+    }
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    // the copy stream must not overtake work of a previous call that still reads the scratch buffers
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[0], ks));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[0], 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    for (int c = 0; c < chunks; c++) {
+        size_t lo = bounds[c], hi = bounds[c + 1], cn = hi - lo;
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_sig + 81 * lo, sigs81 + 81 * lo, cn * 81, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_pk + 96 * lo, pk96 + 96 * lo, cn * 96, cudaMemcpyHostToDevice, cs));
+        if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_inf + lo, pk_inf + lo, cn, cudaMemcpyHostToDevice, cs));
+        size_t b0 = msg_off[lo], b1 = msg_off[hi];
+        if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_m + b0, msgs + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[c], cs));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ks, ctx->ev_chunk[c], 0));
+        soa_batch sc;
+        sc.planes = soa.planes + (size_t)SOA_PLANES * lo;   // a private [11][cn] region per chunk
+        sc.flags = soa.flags + lo;
+        sc.sig_flag = soa.sig_flag + lo;
+        sc.n = cn;
+        k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, ks>>>(cn, (uint8_t*)d_sig + 81 * lo, (uint8_t*)d_pk + 96 * lo,
+                                                                         pk_inf ? (uint8_t*)d_inf + lo : nullptr, sc);
+        cudaEventRecord(ctx->ev_k0, ks);
+        k_verify<<<grid_for(cn, VERIFY_THREADS), VERIFY_THREADS, 0, ks>>>(sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, ctx->gtab,
+                                                                         (uint8_t*)d_out + lo);
+        cudaEventRecord(ctx->ev_k1, ks);
+        ctx->launches += 2;
+        CUDA_TRY(ctx, cudaMemcpyAsync(verdicts + lo, (uint8_t*)d_out + lo, cn, cudaMemcpyDeviceToHost, ks));
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ks));
     return SCHNORR_B200_OK;
 }
 
