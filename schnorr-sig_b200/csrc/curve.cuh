@@ -245,7 +245,9 @@ SB_DEV void bucket_aggregate_odd(const jac_pt* B, int nb, jac_pt* out) {
 // One doubling chain D_j = 2^j P, j = 0..255.  q is consumed in its constant width-w NAF (non-zero odd
 // digits at arbitrary bit positions -> 2^(w-2) buckets of odd multiples, warp-uniform control flow);
 // h in signed 4-bit windows at every fourth step (per-thread digits, uniform trip count).
-SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) {
+// `Dp` is caller-provided storage for the running point D_j (the kernels place it in shared memory: it is
+// touched by every doubling and every addition, i.e. 70 % of the thread-local traffic).
+SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP, jac_pt* Dp) {
     jac_pt Bq[SB_Q_BUCKETS], Bh[8];
 #pragma unroll 1
     for (int b = 0; b < 8; b++) Bh[b] = jac_identity();
@@ -253,16 +255,16 @@ SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP) 
     for (int b = 0; b < SB_Q_BUCKETS; b++) Bq[b] = jac_identity();
     int8_t hd[64];
     recode_signed_w4(h, hd);
-    jac_pt D = P;
+    *Dp = P;
 #pragma unroll 1
     for (int j = 0; j < 256; j++) {
         if ((j & 3) == 0) SB_PHASE_SYNC(1);
-        if (j != 0) jac_dbl_mem(&D);
+        if (j != 0) jac_dbl_mem(Dp);
         int dq = SB_QNAF(j);
-        if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) >> 1], &D, dq < 0);  // warp-uniform
+        if (dq != 0) jac_add_mem(&Bq[(dq < 0 ? -dq : dq) >> 1], Dp, dq < 0);  // warp-uniform
         if ((j & 3) == 0) {
             int dh = hd[j >> 2];
-            if (dh != 0) jac_add_mem(&Bh[(dh < 0 ? -dh : dh) - 1], &D, dh < 0);
+            if (dh != 0) jac_add_mem(&Bh[(dh < 0 ? -dh : dh) - 1], Dp, dh < 0);
         }
     }
     jac_pt tq;

@@ -177,6 +177,12 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
                                                            const uint64_t* __restrict__ msg_off,
                                                            const uint64_t* __restrict__ gtab,
                                                            uint8_t* __restrict__ verdicts) {
+    // running point D_j of each thread: shared memory, padded to 152 B per thread (2-way bank conflicts at most)
+    struct d_slot {
+        jac_pt p;
+        uint64_t pad;
+    };
+    __shared__ d_slot s_d[VERIFY_THREADS];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= in.n) return;
     uint8_t fl = in.flags[i];
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
     uint64_t off = msg_off[i];
     scalar h = sc_zero();
     if (x_ok) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
-    verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab);
+    verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
 }
 
 // ------------------------------------------------------------------------------------------------

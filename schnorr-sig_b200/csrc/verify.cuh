@@ -20,11 +20,11 @@ enum verdict_t : uint8_t {
 // `x_ok` = sig.x limbs canonical (the reference unwraps Fp6::from_bytes AFTER the subgroup check,
 // src/signature.rs:182-186, so an off-subgroup key wins over a malformed x).
 SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
-                             const scalar& h, const uint64_t* __restrict__ gtab) {
+                             const scalar& h, const uint64_t* __restrict__ gtab, jac_pt* d_storage) {
     // [q]P and h*P share one doubling chain (curve.cuh: torsion_check_and_mul); then + e*G from the
     // fixed-base table (multiply_double_with_basepoint_vartime, src/signature.rs:196-198)
     jac_pt r;
-    if (!torsion_check_and_mul(jac_from_affine(pk_x, pk_y, pk_inf), h, &r)) return VERDICT_INVALID_PUBLIC_KEY;
+    if (!torsion_check_and_mul(jac_from_affine(pk_x, pk_y, pk_inf), h, &r, d_storage)) return VERDICT_INVALID_PUBLIC_KEY;
     if (!x_ok) return VERDICT_MALFORMED;
     fixed_base_accumulate(&r, e, gtab);
     return jac_x_equals(r, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;

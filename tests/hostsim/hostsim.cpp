@@ -123,20 +123,21 @@ API void hs_fixed_base_mul(const uint8_t* k32, uint8_t* out96, int* out_inf) {
 }
 API int hs_torsion_free(const uint8_t* p96, int inf) {
     jac_pt r;
-    return torsion_check_and_mul(load_pt(p96, inf), sc_zero(), &r);
+    jac_pt d;
+    return torsion_check_and_mul(load_pt(p96, inf), sc_zero(), &r, &d);
 }
 // h*P + e*G exactly as verify_points composes it
 API void hs_double_base(const uint8_t* p96, int inf, const uint8_t* h32, const uint8_t* e32, uint8_t* out96, int* out_inf) {
     build_gtab();
-    jac_pt r;
-    torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r);
+    jac_pt r, d;
+    torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r, &d);
     fixed_base_accumulate(&r, ldsc(e32), g_gtab.data());
     store_aff(r, out96, out_inf);
 }
 // shared-doubling core: returns the subgroup verdict and h*P
 API int hs_torsion_check_and_mul(const uint8_t* p96, int inf, const uint8_t* h32, uint8_t* out96, int* out_inf) {
-    jac_pt r;
-    bool tf = torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r);
+    jac_pt r, d;
+    bool tf = torsion_check_and_mul(load_pt(p96, inf), ldsc(h32), &r, &d);
     store_aff(r, out96, out_inf);
     return tf;
 }
@@ -165,5 +166,6 @@ API int hs_verify_one(const uint8_t* sig81, const uint8_t* pk96, int pk_inf, con
     if ((!pk_ok && !pk_inf) || sc_geq_q(e)) return VERDICT_MALFORMED;
     scalar h = sc_zero();
     if (x_ok) h = challenge_scalar(sx, px, py, pk_inf != 0, msg, len);
-    return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data());
+    jac_pt d;
+    return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &d);
 }
