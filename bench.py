@@ -62,7 +62,7 @@ def w_per_hash(msg_len):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_verify launch from the ncu --set full capture
 # committed under profiles/ (per launch, keyed by log2 n); None where no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {20: 29.62e9}   # profiles/r1_k_verify_final_ncu.txt: 4.27 GB read + 25.35 GB written (thread-local buckets)
+TRAFFIC_BYTES_PER_LAUNCH = {20: 30.45e9}   # profiles/r1_k_verify_final_ncu.txt: 5.90 GB read + 24.55 GB written (thread-local buckets)
 
 
 def parse_args():
