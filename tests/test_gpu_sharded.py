@@ -89,3 +89,44 @@ def test_keyed_signature_wire_records_and_localisation():
     assert s.verify_batch(sigs, pks, w["msgs"]).is_err()
     loc = s.locate_invalid(sigs, pks, w["msgs"])
     assert [i for i, _ in loc] == [7, 9] and all(e == s.SignatureError(s.SignatureError.InvalidSignature) for _, e in loc)
+
+
+def test_batch_with_skewed_randomisers_exercises_bucket_splitting():
+    """All randomisers equal (and tiny): every s_i R_i term lands in the same bucket of every window, so
+    single buckets hold thousands of points and are split across many segments (k_msm_segment_fixup)."""
+    import schnorr_sig_b200 as s
+    eng = s.default_engine(0)
+    n = 3000
+    w = make_workload(17, n, msg_len=8, nthreads=cref.default_threads())
+    for val in (1, 0x0123456789ABCDEF):
+        rand = np.zeros((n, 32), dtype=np.uint8)
+        rand[:] = np.frombuffer(int(val).to_bytes(32, "little"), dtype=np.uint8)
+        v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], rand)
+        cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], rand, cref.default_threads())
+        assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+    # repeated signer with the SAME message and nonce: identical points with identical scalars (P + P inside a bucket)
+    w2 = {k: (np.repeat(v[:1], 64, axis=0) if isinstance(v, np.ndarray) and v.ndim == 2 else v) for k, v in w.items()}
+    blob = np.tile(w["blob"][:8], 64)
+    off = np.arange(65, dtype=np.uint64) * np.uint64(8)
+    rand = np.repeat(w["rand"][:1], 64, axis=0)
+    v, lhs, rhs = eng.verify_batch(w2["sigs"], w2["pk"], np.zeros(64, np.uint8), blob, off, rand)
+    cv, cl, cr = cref.verify_batch(w2["sigs"], w2["pk"], np.zeros(64, np.uint8), blob, off, rand, 4)
+    assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+
+
+def test_mid_size_random_faults_against_oracle():
+    """2^13 signatures with ragged messages and 1/16 injected faults: verdict vector equals the oracle's."""
+    import schnorr_sig_b200 as s
+    eng = s.default_engine(0)
+    n = 1 << 13
+    lens = [int(x) for x in np.random.default_rng(3).integers(1, 120, n)]
+    w = make_workload(23, n, lens=lens, nthreads=cref.default_threads())
+    w["n"], w["msg_len"] = n, 1
+    f = s.synth.inject_faults(w, every=16)
+    got = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+    want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
+    assert np.array_equal(got, want) and np.array_equal(got, f["expect"])
+    d = eng.hash_messages(f["sigs"][:, :48].copy(), f["pk"], f["blob"], f["off"])
+    ok = f["sigs"][:, :48].view(np.uint64).max(axis=1) < np.uint64(0xFFFFFFFF00000001)
+    cd = cref.hash_messages(f["sigs"][:, :48].copy(), f["pk"], f["blob"], f["off"], cref.default_threads())
+    assert np.array_equal(d[ok], cd[ok])
