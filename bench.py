@@ -38,7 +38,6 @@ import numpy as np  # noqa: E402
 METRIC = "schnorr_verifications_per_sec"
 UNIT = "verifications/s"
 W_PER_VERIFY_L8 = 787338          # SURVEY.md §8(d) canonical cost model v1, 8-byte message
-W_PER_HASH_L8 = 56280
 W_PER_BATCH_SIG = 163900
 HBM_BYTES_PER_VERIFY = 177 + 8 + 8 + 1   # 81 sig + 96 key + msg + offset + verdict
 W_PER_PERMUTATION = 28140
