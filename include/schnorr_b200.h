@@ -58,7 +58,7 @@ int schnorr_b200_synchronize(schnorr_b200_ctx *ctx);
 /* Number of kernel launches issued by this context since creation (bench `gpu_launches`). */
 uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx *ctx);
 /* Device time (CUDA events on the context stream) of the dominant kernel of the last *_dev call:
- * k_verify (verify_many), k_hash (hash_messages), k_msm_bucket_sum (batch).  Synchronises on it. */
+ * k_verify (verify_many), k_hash (hash_messages), k_msm_segment_sum (batch).  Synchronises on it. */
 int schnorr_b200_last_kernel_ms(schnorr_b200_ctx *ctx, float *ms);
 
 /* hash_message(&Fp6, &PublicKey, &[u8]) -> [u8; 32]            src/signature.rs:274-306

@@ -2,8 +2,8 @@
 // src/signature.rs:186,278-282, src/batch.rs:67).  Coefficients c0..c5, canonical.
 //
 // Multiplication: the wrap-around terms (i + j >= 6) use b pre-scaled by 7, so every output
-// coefficient is exactly six 64x64 products accumulated lazily in column accumulators and reduced
-// once (fp.cuh).  24 IMAD.WIDE per coefficient, 144 per multiplication, 84 per squaring.
+// coefficient is exactly six 64x64 products accumulated lazily (even/odd accumulators, fp.cuh) and reduced
+// once.  24 IMAD.WIDE per coefficient: 144 (+5 for the x7 prescale) per multiplication, 87 per squaring.
 #pragma once
 #include "fp.cuh"
 
