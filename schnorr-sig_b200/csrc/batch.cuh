@@ -38,7 +38,10 @@ static msm_plan msm_make_plan(size_t npoints) {
             p.B = 1 << (c - 1);
         }
     }
-    p.chunk_sz = p.B >= 32 ? 32 : p.B;
+    // bucket-reduction chunks: aim at ~8k chunk threads in total (short serial chains), 8..32 buckets each
+    int want = (int)(((double)p.B * p.K) / 8192.0);
+    p.chunk_sz = want >= 32 ? 32 : (want >= 16 ? 16 : 8);
+    if (p.chunk_sz > p.B) p.chunk_sz = p.B;
     p.chunks = p.B / p.chunk_sz;
     return p;
 }
@@ -277,11 +280,11 @@ __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t
     buckets[bucket_of_slot(pl, s)] = acc;
 }
 
-// small multiple m * P by double-and-add (m < 2^20)
+// small multiple m * P (m >= 1) by double-and-add from the top set bit
 __device__ void jac_mul_small_mem(jac_pt* out, const jac_pt* P, uint32_t m) {
-    jac_pt acc = jac_identity();
+    jac_pt acc = *P;
 #pragma unroll 1
-    for (int bit = 19; bit >= 0; bit--) {
+    for (int bit = 30 - __clz(m); bit >= 0; bit--) {
         jac_dbl_mem(&acc);
         if ((m >> bit) & 1) jac_add_mem(&acc, P, false);
     }
@@ -334,17 +337,49 @@ __global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_p
     }
     if (lane == 0) windows[k] = acc;
 }
+// Horner over the windows is a serial chain of ~255 doublings.  Four lanes of one warp share each
+// doubling: the eight squarings of dbl-2007-bl are issued as two rounds of independent squarings on
+// different lanes (SIMT: one instruction stream, lane-dependent operands), the results are exchanged with
+// warp shuffles, and the cheap linear parts are computed redundantly -> 4 field-op levels instead of 9.
+__device__ __forceinline__ fp6 shfl_fp6(const fp6& a, int src) {
+    fp6 r;
+#pragma unroll
+    for (int c = 0; c < 6; c++) r.c[c] = __shfl_sync(0xfu, a.c[c], src);
+    return r;
+}
+__device__ __forceinline__ fp6 pick4(int lane, const fp6& a, const fp6& b, const fp6& c, const fp6& d) {
+    fp6 r;
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.c[k] = lane == 0 ? a.c[k] : (lane == 1 ? b.c[k] : (lane == 2 ? c.c[k] : d.c[k]));
+    return r;
+}
+__device__ void jac_dbl_coop4(jac_pt& p, int lane) {  // lanes 0..3 hold identical copies of p on entry and exit
+    fp6 s1 = fp6_sqr(pick4(lane, p.X, p.Y, p.Z, fp6_add(p.Y, p.Z)));
+    fp6 XX = shfl_fp6(s1, 0), YY = shfl_fp6(s1, 1), ZZ = shfl_fp6(s1, 2), W = shfl_fp6(s1, 3);
+    fp6 s2 = fp6_sqr(pick4(lane, fp6_add(p.X, YY), YY, ZZ, ZZ));
+    fp6 t = shfl_fp6(s2, 0), YYYY = shfl_fp6(s2, 1), Z4 = shfl_fp6(s2, 2);
+    fp6 S = fp6_dbl(fp6_sub(fp6_sub(t, XX), YYYY));
+    fp6 M = fp6_add(fp6_add(fp6_dbl(XX), XX), Z4);
+    jac_pt r;
+    r.X = fp6_sub(fp6_sqr(M), fp6_dbl(S));
+    r.Y = fp6_sub(fp6_mul(M, fp6_sub(S, r.X)), fp6_dbl(fp6_dbl(fp6_dbl(YYYY))));
+    r.Z = fp6_sub(fp6_sub(W, YY), ZZ);
+    p = r;
+}
 // partial192 = Jacobian point (18 u64) || partial scalar sum (4 u64) || bad flag (u64) || pad
-__global__ void k_msm_horner(msm_plan pl, const jac_pt* __restrict__ windows, const uint32_t* __restrict__ lin,
-                             const int* __restrict__ bad, uint64_t* __restrict__ partial) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, const jac_pt* __restrict__ windows,
+                                                   const uint32_t* __restrict__ lin, const int* __restrict__ bad,
+                                                   uint64_t* __restrict__ partial) {
+    int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 4) return;
     jac_pt acc = windows[pl.K - 1];
 #pragma unroll 1
     for (int k = pl.K - 2; k >= 0; k--) {
 #pragma unroll 1
-        for (int s = 0; s < pl.c; s++) jac_dbl_mem(&acc);
-        jac_add_mem(&acc, &windows[k], false);
+        for (int s = 0; s < pl.c; s++) jac_dbl_coop4(acc, lane);
+        jac_add_mem(&acc, &windows[k], false);  // all four lanes redundantly
     }
+    if (lane != 0) return;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
         partial[c] = acc.X.c[c];
@@ -457,7 +492,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
                                                                (seg_partial*)d_parts, buckets);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, 64), 64, 0, st>>>(pl, buckets, chunk_out);
     k_msm_window_fold<<<pl.K, 32, 0, st>>>(pl, chunk_out, windows);
-    k_msm_horner<<<1, 1, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
+    k_msm_horner<<<1, 32, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
     ctx->launches += 12;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
