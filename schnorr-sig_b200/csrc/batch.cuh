@@ -48,7 +48,7 @@ static msm_plan msm_make_plan(size_t npoints) {
 
 // ---- K3 ----------------------------------------------------------------------------------------
 // pts: 2n affine points as 12 x u64 (x||y); scalars: 2n x 8 x u32; lin: n scalars s_i e_i
-__global__ void __launch_bounds__(128) k_batch_prepare(soa_batch in, const uint8_t* __restrict__ msgs,
+__global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const uint8_t* __restrict__ msgs,
                                                        const uint64_t* __restrict__ msg_off,
                                                        const uint8_t* __restrict__ rand32, uint64_t* __restrict__ pts,
                                                        uint32_t* __restrict__ scalars, uint32_t* __restrict__ lin,

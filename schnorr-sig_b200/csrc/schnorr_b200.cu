@@ -28,7 +28,7 @@ using namespace sb;
 // ------------------------------------------------------------------------------------------------
 static constexpr size_t GTAB_U64 = (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 12;
 
-enum scratch_slot { SL_A = 0, SL_B, SL_C, SL_D, SL_E, SL_F, SL_G, SL_H, SL_I, SL_J, SL_K, SL_L, SL_COUNT };
+enum scratch_slot { SL_A = 0, SL_B, SL_C, SL_D, SL_E, SL_F, SL_G, SL_H, SL_I, SL_J, SL_K, SL_L, SL_M, SL_COUNT };
 
 struct schnorr_b200_ctx {
     int device = 0;
@@ -42,6 +42,8 @@ struct schnorr_b200_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
+    bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the affine fast path (A/B measurements, tests)
+    int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
     std::string err;
@@ -176,11 +178,53 @@ static constexpr int VERIFY_THREADS = VERIFY_THREADS_N;
 __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(soa_batch in, const uint8_t* __restrict__ msgs,
                                                            const uint64_t* __restrict__ msg_off,
                                                            const uint64_t* __restrict__ gtab,
-                                                           uint8_t* __restrict__ verdicts) {
+                                                           uint8_t* __restrict__ verdicts,
+                                                           const uint32_t* __restrict__ work_list,
+                                                           const uint32_t* __restrict__ work_count) {
     // running point D_j of each thread: shared memory, padded to 152 B per thread (2-way bank conflicts at most)
     struct d_slot {
         jac_pt p;
         uint64_t pad;
+    };
+    __shared__ d_slot s_d[VERIFY_THREADS];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (work_list) {  // exact pass over the items the affine fast path handed back
+        if (i >= *work_count) return;
+        i = work_list[i];
+    }
+    if (i >= in.n) return;
+    uint8_t fl = in.flags[i];
+    if (fl & FL_MALFORMED) {
+        verdicts[i] = VERDICT_MALFORMED;
+        return;
+    }
+    fp6 sx = load_fp6_planes(in.planes, 0, in.n, i);
+    scalar e = load_scalar_planes(in.planes, 3, in.n, i);
+    fp6 px = load_fp6_planes(in.planes, 5, in.n, i);
+    fp6 py = load_fp6_planes(in.planes, 8, in.n, i);
+    bool pk_inf = fl & FL_PK_INF;
+    bool x_ok = !(fl & FL_X_BAD);
+    uint64_t off = msg_off[i];
+    scalar h = sc_zero();
+    if (x_ok) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+    verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
+}
+
+// K2 fast path: the same verdicts through affine point arithmetic with shared inversions (affine.cuh).
+// Items that meet an exceptional case of the affine group law (identity / small-order keys, colliding
+// partial sums: ~0.1 % of honest inputs) are appended to `work_list` and finished by k_verify.
+#ifndef VERIFY_FAST_MIN_BLOCKS
+#define VERIFY_FAST_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_verify_fast(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                           const uint64_t* __restrict__ msg_off,
+                                                           const uint64_t* __restrict__ gtab,
+                                                           uint8_t* __restrict__ verdicts,
+                                                           uint32_t* __restrict__ work_list,
+                                                           uint32_t* __restrict__ work_count) {
+    struct d_slot {
+        aff_pt p;
+        uint64_t pad;  // 104 B per thread: 2-way bank conflicts at most
     };
     __shared__ d_slot s_d[VERIFY_THREADS];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,8 +242,10 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
     bool x_ok = !(fl & FL_X_BAD);
     uint64_t off = msg_off[i];
     scalar h = sc_zero();
-    if (x_ok) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
-    verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
+    if (x_ok && !pk_inf) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
+    verdicts[i] = v;
+    if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +512,31 @@ static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t by
 
 #include "batch.cuh"
 
+// Signature::verify over an ingested SoA batch: affine fast path, then the exact kernel over the handful of
+// items it handed back.  `list_base` = first element of this batch in the per-call work list (pipelined chunks
+// use disjoint regions), `counter` = index of its counter.
+static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint8_t* msgs, const uint64_t* msg_off,
+                         uint8_t* verdicts, size_t list_base, int counter, size_t list_total, cudaStream_t st) {
+    unsigned grid = grid_for(soa.n, VERIFY_THREADS);
+    if (counter == 0) ctx->exact_counters_used = 0;
+    if (ctx->exact_only) {
+        k_verify<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, nullptr, nullptr);
+        ctx->launches += 1;
+        return 0;
+    }
+    void* wl;
+    if (int rc = ensure_scratch(ctx, SL_M, 4 * (list_total + schnorr_b200_ctx::MAX_CHUNKS), &wl)) return rc;
+    uint32_t* counters = (uint32_t*)wl;
+    uint32_t* list = counters + schnorr_b200_ctx::MAX_CHUNKS + list_base;
+    CUDA_TRY(ctx, cudaMemsetAsync(counters + counter, 0, 4, st));
+    if (counter + 1 > ctx->exact_counters_used) ctx->exact_counters_used = counter + 1;
+    k_verify_fast<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+    // the exact kernel sizes itself from the device-side counter: blocks beyond it exit at once
+    k_verify<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+    ctx->launches += 2;
+    return 0;
+}
+
 extern "C" {
 
 int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
@@ -495,11 +566,15 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     cudaDeviceProp prop;
     CREATE_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        const char* ex = getenv("SB_VERIFY_EXACT");
+        ctx->exact_only = ex && ex[0] == '1';
+    }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     {
         int per_sm = 0;
-        CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verify, VERIFY_THREADS, 0));
+        CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verify_fast, VERIFY_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
         ctx->verify_wave = (size_t)ctx->sm_count * per_sm * VERIFY_THREADS;
     }
@@ -563,6 +638,23 @@ int schnorr_b200_last_kernel_ms(schnorr_b200_ctx* ctx, float* ms) {
     return SCHNORR_B200_OK;
 }
 
+int schnorr_b200_set_exact_only(schnorr_b200_ctx* ctx, int exact_only) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    ctx->exact_only = exact_only != 0;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {
+    if (!ctx || !count) return SCHNORR_B200_EARG;
+    *count = 0;
+    if (ctx->exact_counters_used == 0 || !ctx->scratch[SL_M]) return SCHNORR_B200_OK;
+    uint32_t c[schnorr_b200_ctx::MAX_CHUNKS] = {};
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpy(c, ctx->scratch[SL_M], 4 * ctx->exact_counters_used, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ctx->exact_counters_used; i++) *count += c[i];
+    return SCHNORR_B200_OK;
+}
+
 // ---- hash_messages ---------------------------------------------------------------------------
 int schnorr_b200_hash_messages_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* rx48, const uint8_t* pk96,
                                    const uint8_t* msgs, const uint64_t* msg_off, uint8_t* digests) {
@@ -609,9 +701,9 @@ int schnorr_b200_verify_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t*
     if (int rc = alloc_soa(ctx, n, &soa)) return rc;
     k_ingest<<<grid_for(n, INGEST_THREADS), INGEST_THREADS, 0, ctx->stream>>>(n, sigs81, pk96, pk_inf, soa);
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    k_verify<<<grid_for(n, VERIFY_THREADS), VERIFY_THREADS, 0, ctx->stream>>>(soa, msgs, msg_off, ctx->gtab, verdicts);
+    if (int rc = launch_verify(ctx, soa, msgs, msg_off, verdicts, 0, 0, n, ctx->stream)) return rc;
     cudaEventRecord(ctx->ev_k1, ctx->stream);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
 }
@@ -668,10 +760,9 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, ks>>>(cn, (uint8_t*)d_sig + 81 * lo, (uint8_t*)d_pk + 96 * lo,
                                                                          pk_inf ? (uint8_t*)d_inf + lo : nullptr, sc);
         cudaEventRecord(ctx->ev_k0, ks);
-        k_verify<<<grid_for(cn, VERIFY_THREADS), VERIFY_THREADS, 0, ks>>>(sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, ctx->gtab,
-                                                                         (uint8_t*)d_out + lo);
+        if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, ks)) return rc;
         cudaEventRecord(ctx->ev_k1, ks);
-        ctx->launches += 2;
+        ctx->launches += 1;
         CUDA_TRY(ctx, cudaMemcpyAsync(verdicts + lo, (uint8_t*)d_out + lo, cn, cudaMemcpyDeviceToHost, ks));
     }
     CUDA_TRY(ctx, cudaGetLastError());

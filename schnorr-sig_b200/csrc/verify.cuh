@@ -4,6 +4,7 @@
 //   KeyPair::sign                src/signature.rs:114-129   (device signer: synthetic inputs, §8 f1)
 //   PublicKey::from(&PrivateKey) src/public.rs:26-32
 #pragma once
+#include "affine.cuh"
 #include "curve.cuh"
 #include "rescue.cuh"
 
@@ -14,6 +15,7 @@ enum verdict_t : uint8_t {
     VERDICT_INVALID_PUBLIC_KEY = 1,  // SignatureError::InvalidPublicKey  src/error.rs:15
     VERDICT_INVALID_SIGNATURE = 2,   // SignatureError::InvalidSignature  src/error.rs:17
     VERDICT_MALFORMED = 3,           // inputs on which the reference panics / that its types cannot hold
+    VERDICT_NEEDS_EXACT = 0xff,      // internal: the affine fast path met an exceptional case (never returned to callers)
 };
 
 // Everything after the challenge hash: subgroup check, h*P + e*G, x-only comparison.
@@ -28,6 +30,19 @@ SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const
     if (!x_ok) return VERDICT_MALFORMED;
     fixed_base_accumulate(&r, e, gtab);
     return jac_x_equals(r, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
+}
+
+// Same verdicts through the affine fast path (affine.cuh).  VERDICT_NEEDS_EXACT asks the caller to run
+// verify_points on this item: identity key, or an exceptional case of the affine group law.
+SB_DEV uint8_t verify_points_fast(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
+                                  const scalar& h, const uint64_t* __restrict__ gtab, aff_pt* d_storage) {
+    if (pk_inf) return VERDICT_NEEDS_EXACT;
+    aff_pt r;
+    int fr = verify_core_affine(pk_x, pk_y, h, e, gtab, &r, d_storage);
+    if (fr == FAST_EXCEPTIONAL) return VERDICT_NEEDS_EXACT;
+    if (fr == FAST_NOT_TORSION_FREE) return VERDICT_INVALID_PUBLIC_KEY;
+    if (!x_ok) return VERDICT_MALFORMED;
+    return fp6_eq(r.x, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
 }
 
 // Challenge: h = Scalar::from_bits_vartime(hash_message(R.x, P, m))  (src/signature.rs:188-192).

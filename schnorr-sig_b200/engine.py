@@ -84,6 +84,16 @@ class Engine:
         self._check(self._L.schnorr_b200_last_kernel_ms(self._h, C.byref(ms)), "last_kernel_ms")
         return float(ms.value)
 
+    def set_exact_only(self, flag: bool):
+        """True: every verification goes through the exact Jacobian kernel (A/B measurements, tests)."""
+        self._check(self._L.schnorr_b200_set_exact_only(self._h, 1 if flag else 0), "set_exact_only")
+
+    def last_exact_count(self) -> int:
+        """Items of the last verify_many* call that the affine fast path handed to the exact kernel."""
+        c = C.c_uint64(0)
+        self._check(self._L.schnorr_b200_last_exact_count(self._h, C.byref(c)), "last_exact_count")
+        return int(c.value)
+
     # ---- host-buffer entry points --------------------------------------------------------
     def hash_messages(self, rx48, pk96, msgs, off):
         rx48, pk96, msgs = _u8(rx48, 48), _u8(pk96, 96), _u8(msgs)

@@ -169,3 +169,52 @@ API int hs_verify_one(const uint8_t* sig81, const uint8_t* pk96, int pk_inf, con
     jac_pt d;
     return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &d);
 }
+
+// ---- affine fast path (affine.cuh) ----
+API int hs_fp6_batch_inv(uint64_t* d, int k) { return (int)fp6_batch_inv(reinterpret_cast<fp6*>(d), k); }
+API uint64_t hs_fp_inv_chain(uint64_t a) { return fp_canon(fp_inv_chain(a)); }
+// one batched affine operation list: acc[i] (96 B each, in/out), src[i] (96 B each), mode[i]; is_dbl[i] marks doublings
+API int hs_aff_batch(uint8_t* acc96, const uint8_t* src96, const uint8_t* mode, const uint8_t* is_dbl, int k) {
+    aff_op ops[AFF_MAX_BATCH];
+    for (int i = 0; i < k; i++) {
+        ops[i].acc = reinterpret_cast<aff_pt*>(acc96 + 96 * i);
+        ops[i].src = is_dbl[i] ? nullptr : reinterpret_cast<const aff_pt*>(src96 + 96 * i);
+        ops[i].mode = mode[i];
+    }
+    return aff_batch(ops, k);
+}
+// returns fast_result; out96 = h*P + e*G when FAST_TORSION_FREE / FAST_NOT_TORSION_FREE
+API int hs_verify_core_affine(const uint8_t* p96, const uint8_t* h32, const uint8_t* e32, uint8_t* out96) {
+    build_gtab();
+    fp6 x, y;
+    memcpy(x.c, p96, 48);
+    memcpy(y.c, p96 + 48, 48);
+    aff_pt r, d;
+    memset(&r, 0, sizeof r);
+    int fr = verify_core_affine(x, y, ldsc(h32), ldsc(e32), g_gtab.data(), &r, &d);
+    memcpy(out96, r.x.c, 48);
+    memcpy(out96 + 48, r.y.c, 48);
+    return fr;
+}
+// full per-signature path as k_ingest + k_verify_fast (+ the exact kernel for flagged items) compose it;
+// *used_exact reports whether the fallback ran
+API int hs_verify_one_fast(const uint8_t* sig81, const uint8_t* pk96, int pk_inf, const uint8_t* msg, uint64_t len, int* used_exact) {
+    build_gtab();
+    fp6 sx, px, py;
+    memcpy(sx.c, sig81, 48);
+    memcpy(px.c, pk96, 48);
+    memcpy(py.c, pk96 + 48, 48);
+    scalar e = ldsc(sig81 + 49);
+    bool x_ok = fp6_is_canonical(sx);
+    bool pk_ok = fp6_is_canonical(px) && fp6_is_canonical(py);
+    *used_exact = 0;
+    if ((!pk_ok && !pk_inf) || sc_geq_q(e)) return VERDICT_MALFORMED;
+    scalar h = sc_zero();
+    if (x_ok) h = challenge_scalar(sx, px, py, pk_inf != 0, msg, len);
+    aff_pt da;
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &da);
+    if (v != VERDICT_NEEDS_EXACT) return v;
+    *used_exact = 1;
+    jac_pt d;
+    return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &d);
+}

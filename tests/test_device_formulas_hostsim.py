@@ -256,3 +256,129 @@ def test_shared_doubling_core(hostsim):
             assert (o.INF if oi.value else pt_from96(out)) == o.pt_mul(pt, h)
     H = np.frombuffer((77).to_bytes(32, "little"), dtype=np.uint8).copy()
     assert hostsim.hs_torsion_check_and_mul(p(KAT96), 1, p(H), p(out), C.byref(oi)) == 1 and oi.value == 1
+
+
+# ---- affine fast path (schnorr-sig_b200/csrc/affine.cuh) --------------------------------------------
+
+def test_batch_inversion(hostsim):
+    hostsim.hs_fp_inv_chain.restype = C.c_uint64
+    rng = np.random.default_rng(31)
+    for a in [1, 2, 7, o.P - 1, 2**32, 2**32 - 1] + [int(x) for x in rand_fp(rng, 40) if x]:
+        assert hostsim.hs_fp_inv_chain(C.c_uint64(a)) == pow(a, o.P - 2, o.P)
+    assert hostsim.hs_fp_inv_chain(C.c_uint64(o.P + 5)) == pow(5, o.P - 2, o.P)     # non-canonical representative
+    special = [np.array([1, 0, 0, 0, 0, 0], dtype=np.uint64), np.array([0, 0, 0, 0, 0, 1], dtype=np.uint64),
+               np.array([0, 3, 0, 0, 0, 0], dtype=np.uint64), np.array([o.P - 1] * 6, dtype=np.uint64),
+               np.array([5, 0, 9, 0, 11, 0], dtype=np.uint64)]
+    for k in (1, 2, 3, 4, 7, 10):
+        elems = [rand_fp6(rng) for _ in range(k)]
+        elems[0] = special[k % len(special)]
+        d = np.concatenate(elems).astype(np.uint64)
+        assert hostsim.hs_fp6_batch_inv(p(d), k) == 0
+        for i in range(k):
+            assert tuple(int(x) for x in d[6 * i:6 * i + 6]) == o.f6_inv(tuple(int(x) for x in elems[i]))
+    # zero elements are reported and do not disturb the others
+    elems = [rand_fp6(rng) for _ in range(5)]
+    elems[1] = np.zeros(6, dtype=np.uint64)
+    elems[4] = np.zeros(6, dtype=np.uint64)
+    d = np.concatenate(elems).astype(np.uint64)
+    assert hostsim.hs_fp6_batch_inv(p(d), 5) == 0b10010
+    for i in (0, 2, 3):
+        assert tuple(int(x) for x in d[6 * i:6 * i + 6]) == o.f6_inv(tuple(int(x) for x in elems[i]))
+
+
+def test_affine_batch_operations(hostsim):
+    rng = np.random.default_rng(32)
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 9)] + [kat]
+    NOP, ADD, SUB, SET, SETNEG = 0, 1, 2, 3, 4
+    acc = np.concatenate([pt_to96(a) for a in pts]).copy()
+    src = np.concatenate([pt_to96(pts[(i + 3) % 10]) for i in range(10)]).copy()
+    mode = np.array([ADD, SUB, SET, SETNEG, NOP, ADD, ADD, SUB, ADD, ADD], dtype=np.uint8)
+    dbl = np.array([0, 0, 0, 0, 0, 1, 0, 0, 1, 0], dtype=np.uint8)
+    assert hostsim.hs_aff_batch(p(acc), p(src), p(mode), p(dbl), 10) == 0
+    for i in range(10):
+        a, s = pts[i], pts[(i + 3) % 10]
+        want = {NOP: a, ADD: o.pt_add(a, a) if dbl[i] else o.pt_add(a, s), SUB: o.pt_add(a, o.pt_neg(s)), SET: s,
+                SETNEG: o.pt_neg(s)}[int(mode[i])]
+        assert pt_from96(acc[96 * i:96 * i + 96]) == want
+    # exceptional inputs are reported: P + P, P - P, doubling a point of order 2; inactive slots never are
+    a96 = pt_to96(pts[0])
+    for m, s, d, want in ((ADD, pts[0], 0, 1), (SUB, pts[0], 0, 1), (ADD, o.pt_neg(pts[0]), 0, 1), (NOP, pts[0], 0, 0),
+                          (SET, pts[0], 0, 0)):
+        acc = np.concatenate([a96, pt_to96(pts[1])]).copy()
+        src = np.concatenate([pt_to96(s), pt_to96(pts[2])]).copy()
+        assert hostsim.hs_aff_batch(p(acc), p(src), p(np.array([m, ADD], dtype=np.uint8)), p(np.array([d, 0], dtype=np.uint8)), 2) == want
+        assert pt_from96(acc[96:]) == o.pt_add(pts[1], pts[2])          # the healthy slot is still exact
+    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
+    acc = pt_to96(t2).copy()
+    assert hostsim.hs_aff_batch(p(acc), p(acc.copy()), p(np.array([ADD], dtype=np.uint8)), p(np.array([1], dtype=np.uint8)), 1) == 1
+
+
+def test_verify_core_affine(hostsim):
+    """[q]P == O and h*P + e*G from the affine chain; exceptional keys are reported, never mis-evaluated."""
+    rng = np.random.default_rng(33)
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    n = o.COFACTOR * o.Q
+    out = np.zeros(96, dtype=np.uint8)
+    TF, NTF, EXC = 0, 1, 2
+
+    def run(pt, h, e):
+        H = np.frombuffer(h.to_bytes(32, "little"), dtype=np.uint8).copy()
+        E = np.frombuffer(e.to_bytes(32, "little"), dtype=np.uint8).copy()
+        return hostsim.hs_verify_core_affine(p(pt_to96(pt)), p(H), p(E), p(out))
+
+    good = [o.pt_mul(G, 12345), o.pt_mul(G, int_le(rand_scalars(rng, 1)[0]))]
+    hs = [0, 1, 2, 8, 0x8888888888888888, o.Q - 1, 2**255 - 1] + [int_le(s) for s in rand_scalars(rng, 3)]
+    es = [0, 1, 4096, 4097, o.Q - 1] + [int_le(s) for s in rand_scalars(rng, 2)]
+    for pt in good:
+        for h in hs:
+            for e in es[:3] if h not in hs[-3:] else es:
+                fr = run(pt, h, e)
+                want = o.pt_mul2(pt, h % o.Q if h < o.Q else h, G, e)
+                if want is o.INF:
+                    assert fr == EXC
+                elif fr == EXC:
+                    # tiny / highly regular scalars make two equal partial sums meet (P + P): flagged, never wrong
+                    assert h in (2, 8, 0x8888888888888888, 2**255 - 1), (h, e)
+                else:
+                    assert fr == TF, (h, e)
+                    assert pt_from96(out) == want
+    # h*P + e*G == O  (e = -h*k for P = k*G): the identity result is left to the exact routine
+    assert run(o.pt_mul(G, 5), 3, o.Q - 15) == EXC
+    # off-subgroup key of large order: decided by the fast path
+    fr = run(kat, hs[-1], es[-1])
+    assert fr == NTF and pt_from96(out) == o.pt_mul2(kat, hs[-1], G, es[-1])
+    # small-order / mixed-order adversarial keys: exceptional or a correct "not torsion free"
+    for pt in (o.pt_mul(kat, n // 2), o.pt_mul(kat, n // 10), o.pt_mul(kat, n // 29), o.pt_add(G, o.pt_mul(kat, n // 2)),
+               o.pt_mul(kat, o.Q)):
+        if pt is o.INF:
+            continue
+        fr = run(pt, hs[-2], es[-2])
+        assert fr in (NTF, EXC)
+        if fr == NTF:
+            assert pt_from96(out) == o.pt_mul2(pt, hs[-2], G, es[-2])
+
+
+def test_verify_one_fast_matches_oracle_verdicts(hostsim):
+    lens = [8, 0, 7, 80, 160, 3, 8, 8]
+    w = make_workload(13, len(lens), lens=lens)
+    sigs, pk, inf = w["sigs"].copy(), w["pk"].copy(), w["inf"].copy()
+    sigs[1, 49:] = 0                      # e := 0
+    pk[2] = KAT96                         # off-subgroup key
+    sigs[3, :48] = 0; sigs[3, 48] = 0x80  # x := identity encoding
+    sigs[4, 8:16] = 0xFF                  # non-canonical limb
+    n = o.COFACTOR * o.Q
+    pk[6] = pt_to96(o.pt_mul((o.KAT_X, o.KAT_Y), n // 2))   # key of order 2
+    inf[7] = 1                            # identity key
+    want = cref.verify_many(sigs, pk, inf, w["blob"], w["off"])
+    assert list(want[:6]) == [0, 2, 1, 2, 3, 0] and want[6] == 1
+    used = C.c_int(0)
+    exact_used = []
+    for i, m in enumerate(w["msgs"]):
+        mb = np.frombuffer(m, dtype=np.uint8).copy() if m else np.zeros(1, dtype=np.uint8)
+        got = hostsim.hs_verify_one_fast(p(sigs[i].copy()), p(pk[i].copy()), int(inf[i]), p(mb), C.c_uint64(len(m)), C.byref(used))
+        assert got == want[i], i
+        exact_used.append(used.value)
+    assert exact_used[:6] == [0, 0, 0, 0, 0, 0] and exact_used[6:] == [1, 1]

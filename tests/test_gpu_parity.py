@@ -129,6 +129,33 @@ def test_verify_many_matches_oracle_with_injected_faults(eng, n):
     assert np.array_equal(got, f["expect"])
 
 
+def test_affine_fast_path_agrees_with_exact_kernel_and_hands_back_exceptional_items(eng):
+    """k_verify_fast (affine.cuh) + exact pass == k_verify alone == oracle; the hand-back list is small for honest
+    inputs and contains the adversarial keys."""
+    import schnorr_sig_b200 as s
+    n = 1500
+    w = make_workload(77, n, lens=[int(x) for x in np.random.default_rng(77).integers(0, 30, n)])
+    w["n"], w["msg_len"] = n, 1
+    f = s.synth.inject_faults(w, every=16)
+    kat = (o.KAT_X, o.KAT_Y)
+    order = o.COFACTOR * o.Q
+    f["pk"][3] = pt_to96(o.pt_mul(kat, order // 2))          # order 2: doubling of a 2-torsion point
+    f["pk"][5] = pt_to96(o.pt_mul(kat, order // 29))         # order 29: P + P / P - P inside the buckets
+    f["inf"][7] = 1                                          # identity key
+    want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
+    got_fast = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+    handed_back = eng.last_exact_count()
+    eng.set_exact_only(True)
+    try:
+        got_exact = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        assert eng.last_exact_count() == 0
+    finally:
+        eng.set_exact_only(False)
+    assert np.array_equal(got_fast, want) and np.array_equal(got_exact, want)
+    assert 3 <= handed_back <= 3 + n // 100, handed_back       # the three adversarial keys + ~0.1 % of honest inputs
+    assert not (got_fast == 0xFF).any()
+
+
 def test_verify_empty_and_argument_errors(eng):
     z = np.zeros((0, 81), np.uint8)
     assert eng.verify_many(z, np.zeros((0, 96), np.uint8), None, np.zeros(0, np.uint8), np.zeros(1, np.uint64)).size == 0

@@ -62,6 +62,12 @@ def main():
             if p == "verify":
                 timed("verify", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
                 assert int(d_out.max().item()) == 0
+                print("  handed to the exact kernel: %d of %d" % (eng.last_exact_count(), n), flush=True)
+            elif p == "verify_exact":
+                eng.set_exact_only(True)
+                timed("verify_exact", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
+                eng.set_exact_only(False)
+                assert int(d_out.max().item()) == 0
             elif p == "hash":
                 timed("hash", lambda: eng.hash_messages_dev(n, d_rx, d_pk, d_blob, d_off, d_dig))
             elif p == "batch":
