@@ -196,167 +196,223 @@ SB_DEV_NOINLINE bool aff_batch(const aff_op* ops, int k) {
     return exceptional;
 }
 
+// ---- Jacobian coordinates with the denominator in the BASE field -------------------------------------
+// (X, Y, w), x = X / w^2, y = Y / w^3 with w in Fp*.  The slope of a chord / tangent has a denominator d in Fp6;
+// instead of inverting it, write 1/d = c / n with the cofactor c = n / d in Fp6 and the norm n in Fp (tower
+// Fp6 -> Fp3 -> Fp, ~42 base-field products) and push n into the new w.  Scaling by an Fp element costs 6
+// products (a sixth of an Fp6 multiplication), so
+//     doubling  = 2M + 2S + cofactor + 2 scalings        (Jacobian dbl-2007-bl: 1M + 8S)
+//     addition  = 2M + 1S + cofactor + 7 scalings        (Jacobian add-2007-bl: 11M + 5S)
+// and no field inversion is ever needed.
+struct jf_pt {
+    fp6 X, Y;
+    fp_t w;
+};
+
+// d * c = n,  c in Fp6, n in Fp;  n == 0 <=> d == 0
+SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
+    fp3 a0, a1, adj;
+    fp6_split(*d, a0, a1);
+    fp3 s0 = fp3_sqr6(a0), s1 = fp3_sqr6(a1);
+    // N = a0^2 - v a1^2 in Fp3,  v (x0, x1, x2) = (7 x2, x0, x1);   1/d = (a0 - a1 u) / N
+    fp3 nn = fp3{{fp_sub(s0.c[0], fp_mul7(s1.c[2])), fp_sub(s0.c[1], s1.c[0]), fp_sub(s0.c[2], s1.c[1])}};
+    fp3_adj_norm_lazy(nn, adj, *n);  // 1/N = adj / n
+    fp3 na1 = fp3{{FP_P - a1.c[0], FP_P - a1.c[1], FP_P - a1.c[2]}};
+    *c = fp6_join(fp3_mul(a0, adj), fp3_mul(na1, adj));
+}
+
+// a * s for s in Fp (any 64-bit representative)
+SB_DEV_NOINLINE fp6 fp6_scale(fp6 a, fp_t s) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) r.c[i] = fp_mul(a.c[i], s);
+    return r;
+}
+// a * s - b * t  (s, t any 64-bit representatives; a, b canonical)
+SB_DEV_NOINLINE fp6 fp6_scale_diff(fp6 a, fp_t s, fp6 b, fp_t t) {
+    fp6 r;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        wide_acc w;
+        wide_zero(w);
+        wide_mac(w, a.c[i], s);
+        wide_mac(w, FP_P - b.c[i], t);
+        r.c[i] = wide_reduce(w);
+    }
+    return r;
+}
+
+// p <- 2 p.  Returns true on the exceptional input (a point of order 2: the result would be the identity).
+SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
+    fp6 X = p->X, Y = p->Y;
+    fp_t w = p->w;
+    fp6 d = fp6_dbl(Y), c;
+    fp_t n;
+    fp6_cofactor_norm(&d, &c, &n);
+    fp_t w4 = fp_sqr(fp_sqr_nc(w));
+    fp6 xx = fp6_sqr(X);
+    fp6 num = fp6_add(fp6_dbl(xx), xx);
+    num.c[0] = fp_add(num.c[0], w4);        // 3 X^2 + a w^4, a = 1
+    fp6 L = fp6_mul(num, c);                // slope = L / (n w)
+    fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
+    fp6 A = fp6_scale(X, n2);
+    fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
+    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, n3));
+    p->X = X3;
+    p->Y = Y3;
+    p->w = fp_mul(n, w);
+    return n == 0;
+}
+
+// Per-thread mode of an addition (data-dependent, evaluated with selects: control flow stays uniform)
+enum jf_mode : uint8_t {
+    JOP_NOP = 0,     // leave acc unchanged (the addend is the identity / a zero digit)
+    JOP_ADD = 1,     // acc <- acc + src
+    JOP_SUB = 2,     // acc <- acc - src
+    JOP_SET = 3,     // acc <- src   (acc was the identity)
+    JOP_SETNEG = 4,  // acc <- -src
+};
+SB_DEV uint8_t jf_add_mode(bool acc_empty, bool src_empty, bool neg) {
+    return src_empty ? JOP_NOP : (acc_empty ? (neg ? JOP_SETNEG : JOP_SET) : (neg ? JOP_SUB : JOP_ADD));
+}
+
+// acc <- acc (+|-) src according to `mode`.  Returns true when an ACTIVE addition met x(acc) == x(src)
+// (P + P or P - P): the fast path cannot represent / evaluate those and must be abandoned.
+SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
+    fp6 X1 = acc->X, Y1 = acc->Y, X2 = src->X, Y2 = src->Y;
+    fp_t w1 = acc->w, w2 = src->w;
+    if (mode == JOP_SUB || mode == JOP_SETNEG) Y2 = fp6_neg(Y2);
+    fp_t w1s = fp_sqr_nc(w1), w1c = fp_mul_nc(w1s, w1), w2s = fp_sqr_nc(w2), w2c = fp_mul_nc(w2s, w2);
+    fp6 d = fp6_scale_diff(X1, w2s, X2, w1s);    // U1 - U2,  U1 = X1 w2^2,  U2 = X2 w1^2
+    fp6 num = fp6_scale_diff(Y1, w2c, Y2, w1c);  // S1 - S2
+    fp6 c;
+    fp_t n;
+    fp6_cofactor_norm(&d, &c, &n);
+    fp6 L = fp6_mul(num, c);                     // slope = L / (n w1 w2)
+    fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
+    fp6 A = fp6_scale(X1, fp_mul_nc(n2, w2s));   // n^2 U1 = x1 w3^2
+    fp6 B = fp6_scale(X2, fp_mul_nc(n2, w1s));   // n^2 U2 = x2 w3^2
+    fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), B);
+    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));   // ... - y1 w3^3
+    fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
+    bool active = mode == JOP_ADD || mode == JOP_SUB;
+    bool set = mode == JOP_SET || mode == JOP_SETNEG;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        acc->X.c[i] = active ? X3.c[i] : (set ? X2.c[i] : X1.c[i]);
+        acc->Y.c[i] = active ? Y3.c[i] : (set ? Y2.c[i] : Y1.c[i]);
+    }
+    acc->w = active ? w3 : (set ? w2 : w1);
+    return active && n == 0;
+}
+
+// a == b as points (both finite)
+SB_DEV bool jf_eq_neg(const jf_pt& a, const jf_pt& b, bool& x_eq) {
+    fp_t was = fp_sqr_nc(a.w), wbs = fp_sqr_nc(b.w);
+    x_eq = fp6_eq(fp6_scale(a.X, wbs), fp6_scale(b.X, was));
+    return x_eq && fp6_eq(fp6_scale(a.Y, fp_mul_nc(wbs, b.w)), fp6_neg(fp6_scale(b.Y, fp_mul_nc(was, a.w))));
+}
+
 enum fast_result : int {
     FAST_TORSION_FREE = 0,      // [q]P == O, h*P + e*G computed
     FAST_NOT_TORSION_FREE = 1,  // [q]P != O
     FAST_EXCEPTIONAL = 2,       // an exceptional case was met: use the exact routine
 };
 
-// [q]P == O ?  and  R = h*P + e*G  (affine), sharing the doubling chain D_j = 2^j P as torsion_check_and_mul
-// does, but with every point affine.  `Dp` is caller-provided storage for D_j (shared memory in the kernels).
-// On FAST_TORSION_FREE, *R is the result (never the identity: that case is reported as exceptional).
-SB_DEV int verify_core_affine(const fp6& px, const fp6& py, const scalar& h, const scalar& e,
-                              const uint64_t* __restrict__ gtab, aff_pt* R, aff_pt* Dp) {
-    aff_pt W[GTAB_WINDOWS];  // buckets during the chain (Bq = W[0..8), Bh = W[8..16)), table points afterwards
-    aff_pt* Bq = W;
-    aff_pt* Bh = W + 8;
-    aff_op ops[AFF_MAX_BATCH];
+// [q]P == O ?  and  R = h*P + e*G, sharing the doubling chain D_j = 2^j P as torsion_check_and_mul does, in the
+// (X, Y, w) coordinates above.  `Dp` is caller-provided storage for D_j (shared memory in the kernels).
+// On FAST_TORSION_FREE / FAST_NOT_TORSION_FREE, *R is the result (never the identity: that is reported as exceptional).
+SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const scalar& e,
+                            const uint64_t* __restrict__ gtab, jf_pt* R, jf_pt* Dp) {
+    jf_pt Bq[8], Bh[8];
     int8_t hd[64];
     recode_signed_w4(h, hd);
     uint32_t q_seen = 0, h_seen = 0;
     bool exc = false;
 #pragma unroll 1
-    for (int b = 0; b < 16; b++) W[b] = aff_pt{fp6_zero(), fp6_zero()};  // dummy operations read empty buckets
-    Dp->x = px;
-    Dp->y = py;
+    for (int b = 0; b < 8; b++) {  // dummy (masked) operations read empty buckets: give them defined contents
+        Bq[b] = jf_pt{fp6_zero(), fp6_zero(), 1};
+        Bh[b] = Bq[b];
+    }
+    Dp->X = px;
+    Dp->Y = py;
+    Dp->w = 1;
 #pragma unroll 1
     for (int j = 0; j < 256; j++) {
         if ((j & 3) == 0) SB_PHASE_SYNC(1);
-        int k = 0;
         int dq = SB_QWNAF(j);
         if (dq != 0) {  // warp-uniform
             int idx = (dq < 0 ? -dq : dq) >> 1;
-            ops[k].acc = &Bq[idx];
-            ops[k].src = Dp;
-            ops[k].mode = aff_add_mode(!((q_seen >> idx) & 1), false, dq < 0);
+            exc |= jf_add(&Bq[idx], Dp, jf_add_mode(!((q_seen >> idx) & 1), false, dq < 0));
             q_seen |= 1u << idx;
-            k++;
         }
         if ((j & 3) == 0) {
             int dh = hd[j >> 2];
             int mag = dh < 0 ? -dh : dh;
             int idx = mag ? mag - 1 : 0;
-            ops[k].acc = &Bh[idx];
-            ops[k].src = Dp;
-            ops[k].mode = aff_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0);
+            exc |= jf_add(&Bh[idx], Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
             if (mag) h_seen |= 1u << idx;
-            k++;
         }
-        if (j < 255) {
-            ops[k].acc = Dp;
-            ops[k].src = nullptr;
-            ops[k].mode = AOP_ADD;
-            k++;
-        }
-        if (k) exc |= aff_batch(ops, k);
+        if (j < 255) exc |= jf_dbl(Dp);
     }
-    // Bucket aggregation, both scalars in lockstep (R_k = sum_{m>=k} B_m, O_k = sum_{m>=k} R_m):
+    // Bucket aggregation (R_k = sum_{m>=k} B_m, O_k = sum_{m>=k} R_m):
     //   q (odd digits 2k+1):  [q]P = 2 O_1 + R_0        h (digits m = k+1):  h*P = O_0
-    aff_pt Rq = Bq[7], Oq = Bq[7], Rh = Bh[7], Oh = Bh[7];
+    jf_pt Rq = Bq[7], Oq = Bq[7], Rh = Bh[7], Oh = Bh[7];
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
 #pragma unroll 1
-    for (int t = 1; t <= 8; t++) {
+    for (int b = 6; b >= 0; b--) {
         SB_PHASE_SYNC(1);
-        int k = 0;
-        if (t >= 2) {  // O += R (the value of R before this round's update)
-            if (t <= 7) {
-                ops[k].acc = &Oq;
-                ops[k].src = &Rq;
-                ops[k].mode = aff_add_mode(eOq, eRq, false);
-                eOq = eOq && eRq;
-            } else {  // t == 8: O_q <- 2 O_1
-                ops[k].acc = &Oq;
-                ops[k].src = nullptr;
-                ops[k].mode = eOq ? AOP_NOP : AOP_ADD;
-            }
-            k++;
-            ops[k].acc = &Oh;
-            ops[k].src = &Rh;
-            ops[k].mode = aff_add_mode(eOh, eRh, false);
-            eOh = eOh && eRh;
-            k++;
+        bool eb = !((q_seen >> b) & 1);
+        exc |= jf_add(&Rq, &Bq[b], jf_add_mode(eRq, eb, false));
+        eRq = eRq && eb;
+        if (b >= 1) {
+            exc |= jf_add(&Oq, &Rq, jf_add_mode(eOq, eRq, false));
+            eOq = eOq && eRq;
         }
-        if (t <= 7) {  // R += B_{7-t}
-            int b = 7 - t;
-            bool eb = !((q_seen >> b) & 1);
-            ops[k].acc = &Rq;
-            ops[k].src = &Bq[b];
-            ops[k].mode = aff_add_mode(eRq, eb, false);
-            eRq = eRq && eb;
-            k++;
-            eb = !((h_seen >> b) & 1);
-            ops[k].acc = &Rh;
-            ops[k].src = &Bh[b];
-            ops[k].mode = aff_add_mode(eRh, eb, false);
-            eRh = eRh && eb;
-            k++;
-        }
-        exc |= aff_batch(ops, k);
+        eb = !((h_seen >> b) & 1);
+        exc |= jf_add(&Rh, &Bh[b], jf_add_mode(eRh, eb, false));
+        eRh = eRh && eb;
+        exc |= jf_add(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
+        eOh = eOh && eRh;
     }
-    // [q]P = Oq + Rq is the identity  <=>  Oq == -Rq
-    bool x_eq = fp6_eq(Oq.x, Rq.x);
-    bool y_opp = fp6_eq(Oq.y, fp6_neg(Rq.y));
-    if (eOq || eRq) exc = true;                // degenerate digit pattern: leave it to the exact routine
-    if (x_eq && !y_opp) exc = true;            // 2 O_1 == R_0: a doubling
-    bool torsion_free = x_eq && y_opp;
+    if (eOq || eRq) exc = true;  // degenerate digit pattern: leave it to the exact routine
+    else exc |= jf_dbl(&Oq);
+    // [q]P = 2 O_1 + R_0 is the identity  <=>  2 O_1 == -R_0
+    bool x_eq;
+    bool torsion_free = jf_eq_neg(Oq, Rq, x_eq);
+    if (x_eq && !torsion_free) exc = true;  // 2 O_1 == R_0: a doubling the fast path does not evaluate
 
-    // e*G: the 20 table points and h*P summed as a tree (5 shared inversions)
-    aff_pt hP = Oh;
-    bool e_hP = eOh;
-    uint32_t t_empty = 0;
+    // + e*G: 20 table points (affine, w = 1) added to h*P
+    bool e_acc = eOh;
+    *R = Oh;
     {
         int carry = 0;
+        jf_pt T;
+        T.w = 1;
 #pragma unroll 1
         for (int i = 0; i < GTAB_WINDOWS; i++) {
+            if ((i & 3) == 0) SB_PHASE_SYNC(1);
             int raw = (int)sc_bits(e, GTAB_W * i, GTAB_W) + carry;
             bool neg = raw > (1 << (GTAB_W - 1));
             carry = neg ? 1 : 0;
-            int d = neg ? (1 << GTAB_W) - raw : raw;
-            const uint64_t* ent = gtab + ((size_t)i * GTAB_ENTRIES + (d ? d : 1)) * GTAB_ENTRY_U64;
-            fp6 qx, qy;
+            int dg = neg ? (1 << GTAB_W) - raw : raw;
+            const uint64_t* ent = gtab + ((size_t)i * GTAB_ENTRIES + (dg ? dg : 1)) * GTAB_ENTRY_U64;
 #if defined(__CUDA_ARCH__)
             const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(ent);
             ulonglong2 a = e2[0], b = e2[1], c = e2[2], dd = e2[3], ee = e2[4], f = e2[5];
-            qx = fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
-            qy = fp6{{dd.x, dd.y, ee.x, ee.y, f.x, f.y}};
+            T.X = fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
+            T.Y = fp6{{dd.x, dd.y, ee.x, ee.y, f.x, f.y}};
 #else
             for (int c = 0; c < 6; c++) {
-                qx.c[c] = ent[c];
-                qy.c[c] = ent[6 + c];
+                T.X.c[c] = ent[c];
+                T.Y.c[c] = ent[6 + c];
             }
 #endif
-            if (neg) qy = fp6_neg(qy);
-            W[i].x = qx;
-            W[i].y = qy;
-            if (d == 0) t_empty |= 1u << i;
+            exc |= jf_add(R, &T, jf_add_mode(e_acc, dg == 0, neg));
+            e_acc = e_acc && dg == 0;
         }
     }
-    // level strides 1, 2, 4, 8, 16 over W[0..20); h*P joins W[16] at the third level
-#pragma unroll 1
-    for (int lvl = 0; lvl < 5; lvl++) {
-        SB_PHASE_SYNC(1);
-        int stride = 1 << lvl, k = 0;
-#pragma unroll 1
-        for (int i = 0; i + stride < GTAB_WINDOWS; i += 2 * stride) {
-            bool ea = (t_empty >> i) & 1, eb = (t_empty >> (i + stride)) & 1;
-            ops[k].acc = &W[i];
-            ops[k].src = &W[i + stride];
-            ops[k].mode = aff_add_mode(ea, eb, false);
-            if (!(ea && eb)) t_empty &= ~(1u << i);
-            k++;
-        }
-        if (lvl == 2) {
-            bool ea = (t_empty >> 16) & 1;
-            ops[k].acc = &W[16];
-            ops[k].src = &hP;
-            ops[k].mode = aff_add_mode(ea, e_hP, false);
-            if (!(ea && e_hP)) t_empty &= ~(1u << 16);
-            k++;
-        }
-        exc |= aff_batch(ops, k);
-    }
-    if (t_empty & 1) exc = true;  // the result is the identity: exact routine
-    *R = W[0];
+    if (e_acc) exc = true;  // the result is the identity: exact routine
     if (exc) return FAST_EXCEPTIONAL;
     return torsion_free ? FAST_TORSION_FREE : FAST_NOT_TORSION_FREE;
 }

@@ -223,8 +223,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
                                                            uint32_t* __restrict__ work_list,
                                                            uint32_t* __restrict__ work_count) {
     struct d_slot {
-        aff_pt p;
-        uint64_t pad;  // 104 B per thread: 2-way bank conflicts at most
+        jf_pt p;  // 104 B per thread: 2-way bank conflicts at most
     };
     __shared__ d_slot s_d[VERIFY_THREADS];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -35,14 +35,15 @@ SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const
 // Same verdicts through the affine fast path (affine.cuh).  VERDICT_NEEDS_EXACT asks the caller to run
 // verify_points on this item: identity key, or an exceptional case of the affine group law.
 SB_DEV uint8_t verify_points_fast(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
-                                  const scalar& h, const uint64_t* __restrict__ gtab, aff_pt* d_storage) {
+                                  const scalar& h, const uint64_t* __restrict__ gtab, jf_pt* d_storage) {
     if (pk_inf) return VERDICT_NEEDS_EXACT;
-    aff_pt r;
-    int fr = verify_core_affine(pk_x, pk_y, h, e, gtab, &r, d_storage);
+    jf_pt r;
+    int fr = verify_core_fast(pk_x, pk_y, h, e, gtab, &r, d_storage);
     if (fr == FAST_EXCEPTIONAL) return VERDICT_NEEDS_EXACT;
     if (fr == FAST_NOT_TORSION_FREE) return VERDICT_INVALID_PUBLIC_KEY;
     if (!x_ok) return VERDICT_MALFORMED;
-    return fp6_eq(r.x, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
+    // x(R) == sig.x  <=>  X == sig.x w^2   (src/signature.rs:200)
+    return fp6_eq(r.X, fp6_scale(sig_x, fp_sqr_nc(r.w))) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
 }
 
 // Challenge: h = Scalar::from_bits_vartime(hash_message(R.x, P, m))  (src/signature.rs:188-192).

@@ -189,11 +189,15 @@ API int hs_verify_core_affine(const uint8_t* p96, const uint8_t* h32, const uint
     fp6 x, y;
     memcpy(x.c, p96, 48);
     memcpy(y.c, p96 + 48, 48);
-    aff_pt r, d;
+    jf_pt r, d;
     memset(&r, 0, sizeof r);
-    int fr = verify_core_affine(x, y, ldsc(h32), ldsc(e32), g_gtab.data(), &r, &d);
-    memcpy(out96, r.x.c, 48);
-    memcpy(out96 + 48, r.y.c, 48);
+    r.w = 1;
+    int fr = verify_core_fast(x, y, ldsc(h32), ldsc(e32), g_gtab.data(), &r, &d);
+    // normalise (X, Y, w) for the comparison with the oracle
+    fp_t wi = fp_inv(fp_canon(r.w)), wi2 = fp_sqr(wi);
+    fp6 ax = fp6_scale(r.X, wi2), ay = fp6_scale(r.Y, fp_mul(wi2, wi));
+    memcpy(out96, ax.c, 48);
+    memcpy(out96 + 48, ay.c, 48);
     return fr;
 }
 // full per-signature path as k_ingest + k_verify_fast (+ the exact kernel for flagged items) compose it;
@@ -211,10 +215,48 @@ API int hs_verify_one_fast(const uint8_t* sig81, const uint8_t* pk96, int pk_inf
     if ((!pk_ok && !pk_inf) || sc_geq_q(e)) return VERDICT_MALFORMED;
     scalar h = sc_zero();
     if (x_ok) h = challenge_scalar(sx, px, py, pk_inf != 0, msg, len);
-    aff_pt da;
+    jf_pt da;
     uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &da);
     if (v != VERDICT_NEEDS_EXACT) return v;
     *used_exact = 1;
     jac_pt d;
     return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &d);
+}
+
+// one (X, Y, w) operation on affine inputs given a scrambling denominator: in/out as affine 96-byte points
+static jf_pt jf_from_affine(const uint8_t* p96, uint64_t w) {
+    jf_pt r;
+    fp6 x, y;
+    memcpy(x.c, p96, 48);
+    memcpy(y.c, p96 + 48, 48);
+    fp_t w2 = fp_sqr(w);
+    r.X = fp6_scale(x, w2);
+    r.Y = fp6_scale(y, fp_mul(w2, w));
+    r.w = w;
+    return r;
+}
+static void jf_to_affine(const jf_pt& r, uint8_t* out96) {
+    fp_t wi = fp_inv(fp_canon(r.w)), wi2 = fp_sqr(wi);
+    fp6 ax = fp6_scale(r.X, wi2), ay = fp6_scale(r.Y, fp_mul(wi2, wi));
+    memcpy(out96, ax.c, 48);
+    memcpy(out96 + 48, ay.c, 48);
+}
+API int hs_jf_add(const uint8_t* a96, uint64_t wa, const uint8_t* b96, uint64_t wb, int mode, uint8_t* out96) {
+    jf_pt a = jf_from_affine(a96, wa), b = jf_from_affine(b96, wb);
+    bool exc = jf_add(&a, &b, (uint8_t)mode);
+    jf_to_affine(a, out96);
+    return exc;
+}
+API int hs_jf_dbl(const uint8_t* a96, uint64_t wa, uint8_t* out96) {
+    jf_pt a = jf_from_affine(a96, wa);
+    bool exc = jf_dbl(&a);
+    if (!exc) jf_to_affine(a, out96);
+    return exc;
+}
+API uint64_t hs_fp6_cofactor_norm(const uint64_t* d, uint64_t* c) {
+    fp6 dd = ld6(d), cc;
+    fp_t n;
+    fp6_cofactor_norm(&dd, &cc, &n);
+    st6(c, cc);
+    return n;
 }

@@ -382,3 +382,37 @@ def test_verify_one_fast_matches_oracle_verdicts(hostsim):
         assert got == want[i], i
         exact_used.append(used.value)
     assert exact_used[:6] == [0, 0, 0, 0, 0, 0] and exact_used[6:] == [1, 1]
+
+
+def test_fp_denominator_jacobian_operations(hostsim):
+    """(X, Y, w) coordinates with w in Fp (affine.cuh: jf_dbl / jf_add / fp6_cofactor_norm)."""
+    hostsim.hs_fp6_cofactor_norm.restype = C.c_uint64
+    rng = np.random.default_rng(41)
+    c = np.zeros(6, dtype=np.uint64)
+    for d in [rand_fp6(rng) for _ in range(20)] + [np.array([1, 0, 0, 0, 0, 0], dtype=np.uint64),
+                                                   np.array([0, 0, 0, 0, 0, o.P - 1], dtype=np.uint64),
+                                                   np.array([0, 3, 0, 0, 0, 0], dtype=np.uint64)]:
+        n = hostsim.hs_fp6_cofactor_norm(p(d), p(c))
+        td = tuple(int(x) for x in d)
+        assert n != 0 and o.f6_mul(td, tuple(int(x) for x in c)) == (n, 0, 0, 0, 0, 0)
+    assert hostsim.hs_fp6_cofactor_norm(p(np.zeros(6, dtype=np.uint64)), p(c)) == 0
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 5)] + [kat, G]
+    ws = [1, 2, o.P - 1, 0x123456789abcdef] + [int(x) for x in rand_fp(rng, 3)]
+    out = np.zeros(96, dtype=np.uint8)
+    NOP, ADD, SUB, SET, SETNEG = 0, 1, 2, 3, 4
+    for i, a in enumerate(pts):
+        wa, wb = ws[i % len(ws)], ws[(3 * i + 1) % len(ws)]
+        b = pts[(i + 2) % len(pts)]
+        A, B = pt_to96(a), pt_to96(b)
+        assert hostsim.hs_jf_dbl(p(A), C.c_uint64(wa), p(out)) == 0 and pt_from96(out) == o.pt_add(a, a)
+        for mode, want in ((ADD, o.pt_add(a, b)), (SUB, o.pt_add(a, o.pt_neg(b))), (SET, b), (SETNEG, o.pt_neg(b)), (NOP, a)):
+            assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(B), C.c_uint64(wb), mode, p(out)) == 0
+            assert pt_from96(out) == want, (i, mode)
+        # exceptional inputs are reported when active, ignored when masked
+        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), ADD, p(out)) == 1
+        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), SUB, p(out)) == 1
+        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), NOP, p(out)) == 0 and pt_from96(out) == a
+    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
+    assert hostsim.hs_jf_dbl(p(pt_to96(t2)), C.c_uint64(5), p(out)) == 1
