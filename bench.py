@@ -13,7 +13,7 @@ seeded generator (synthetic), one invalid signature per 1024 injected (SURVEY.md
  e2e        same metric through the public host API (pinned host buffers, H2D + kernels + D2H inside
             the timed region)
  roofline   integer-multiply pipe ("imad"): canonical wide multiplies per verification (SURVEY.md §8d
-            cost model v1: 787 338) x verifications per launch / k_verify device time, against the
+            cost model v1: 787 338) x verifications per launch / k_verify_fast device time, against the
             peak measured live by the engine's own IMAD.WIDE calibration kernel (K6) -- HBM and tensor
             cores are not the bound of this path; the HBM fraction is reported alongside.
  cpu_baseline / --impl reference
@@ -42,6 +42,10 @@ W_PER_BATCH_SIG = 163900
 HBM_BYTES_PER_VERIFY = 177 + 8 + 8 + 1   # 81 sig + 96 key + msg + offset + verdict
 W_PER_PERMUTATION = 28140
 W_VERIFY_WITHOUT_HASH = W_PER_VERIFY_L8 - 2 * W_PER_PERMUTATION
+# multiplies the kernels actually EXECUTE per verification (counted by the test-only counter of the host build of the
+# device headers, tests/test_device_formulas_hostsim.py::test_executed_multiply_counts_match_design_doc)
+W_EXECUTED_FAST_L8 = 336813       # k_verify_fast: (X, Y, w) coordinates, 8-byte message (2 permutations)
+W_EXECUTED_PER_PERMUTATION = 28000
 
 
 def permutations_for(msg_len):
@@ -59,9 +63,9 @@ def w_per_hash(msg_len):
     return permutations_for(msg_len) * W_PER_PERMUTATION
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_verify launch from the ncu --set full capture
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_verify_fast launch from the ncu --set full capture
 # committed under profiles/ (per launch, keyed by log2 n); None where no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {20: 30.45e9}   # profiles/r1_k_verify_final_ncu.txt: 5.90 GB read + 24.55 GB written (thread-local buckets)
+TRAFFIC_BYTES_PER_LAUNCH = {20: 8.855e9, 17: 1.026e9}   # profiles/r1_k_verify_fast_ncu.txt (n = 2^20): 1.06 GB read + 7.80 GB written (thread-local buckets)
 
 
 def parse_args():
@@ -324,7 +328,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / (float(t.item()) * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_verify) ---------------------------------------------
+    # ---- roofline of the dominant kernel (k_verify_fast; the exact pass over handed-back items is inside kernel_ms) ----
     peak_w, peak_ms = eng.imad_peak(1 << 15)
     k_ms = float(np.mean(kernel_ms))
     achieved_w = n * w_per_verify(L) / (k_ms * 1e-3)
@@ -338,7 +342,8 @@ def main():
     hbm_achieved = n * (HBM_BYTES_PER_VERIFY - 8 + L) / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "imad", "achieved": (achieved_w or 0) / 1e12, "peak": peak_w / 1e12, "unit": "Tmul32x32/s",
                 "frac": achieved_w / peak_w, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.log2n),
-                "kernel": "k_verify", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / dev_ms,
+                "frac_executed": n * (W_EXECUTED_FAST_L8 + (permutations_for(L) - 2) * W_EXECUTED_PER_PERMUTATION) / (k_ms * 1e-3) / peak_w,
+                "kernel": "k_verify_fast", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / dev_ms,
                 "peak_source": "measured live: schnorr_b200_imad_peak (K6, IMAD.WIDE.U32 chains, full grid)",
                 "peak_nominal": 148 * 32 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12 if True else None,
                 "algorithmic_units": "%d wide multiplies per verification (SURVEY.md 8d cost model v1, %d-byte message) x %d per launch" % (w_per_verify(L), L, n),

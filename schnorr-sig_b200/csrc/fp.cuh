@@ -24,6 +24,14 @@
 
 namespace sb {
 
+// TEST-ONLY (tests/hostsim): count the 32x32->64 multiplies an algorithm executes, for the cost figures in DESIGN.md
+#if !defined(__CUDA_ARCH__) && defined(SB_COUNT_WIDE)
+static unsigned long long g_wide_count = 0;
+#define SB_WIDE(n) (g_wide_count += (n))
+#else
+#define SB_WIDE(n) ((void)0)
+#endif
+
 typedef uint64_t fp_t;
 static constexpr uint64_t FP_P = 0xffffffff00000001ULL;
 static constexpr uint64_t FP_EPS = 0xffffffffULL;  // 2^64 mod p
@@ -137,6 +145,7 @@ SB_DEV void wide_mac(wide_acc& w, uint64_t a, uint64_t b) {
         : "+r"(w.e0), "+r"(w.e1), "+r"(w.e2), "+r"(w.e3), "+r"(w.e4), "+r"(w.o1), "+r"(w.o2), "+r"(w.o3)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 #else
+    SB_WIDE(4);
     typedef unsigned __int128 u128;
     u128 e_lo = ((u128)w.e2 << 64) | ((uint64_t)w.e1 << 32) | w.e0;   // e0..e2 (96 bits) + carries into e3,e4
     u128 E = e_lo + ((u128)w.e3 << 96);
@@ -177,6 +186,7 @@ SB_DEV void wide_mac_sqr(wide_acc& w, uint64_t a) {
         : "+r"(w.e0), "+r"(w.e1), "+r"(w.e2), "+r"(w.e3), "+r"(w.e4), "+r"(w.o1), "+r"(w.o2), "+r"(w.o3)
         : "r"(a0), "r"(a1));
 #else
+    SB_WIDE(-1);  // the device form has three products
     wide_mac(w, a, a);
 #endif
 }
@@ -252,6 +262,7 @@ SB_DEV fp_t fp_mul_nc(fp_t a, fp_t b) {
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return ((uint64_t)t1 << 32) | t0;
 #else
+    SB_WIDE(4);
     return (fp_t)(((unsigned __int128)a * b) % FP_P);
 #endif
 }
@@ -290,6 +301,7 @@ SB_DEV fp_t fp_sqr_nc(fp_t a) {
         : "r"(a0), "r"(a1));
     return ((uint64_t)t1 << 32) | t0;
 #else
+    SB_WIDE(3);
     return (fp_t)(((unsigned __int128)a * a) % FP_P);
 #endif
 }
@@ -297,6 +309,7 @@ SB_DEV fp_t fp_mul(fp_t a, fp_t b) { return fp_canon(fp_mul_nc(a, b)); }
 SB_DEV fp_t fp_sqr(fp_t a) { return fp_canon(fp_sqr_nc(a)); }
 // a * k for a small constant k < 2^32
 SB_DEV fp_t fp_mul_small(fp_t a, uint32_t k) {
+    SB_WIDE(2);
     uint64_t lo = (uint64_t)(uint32_t)a * k;
     uint64_t hi = (a >> 32) * k;  // weight 2^32
     uint64_t s = lo + (hi << 32);

@@ -3,6 +3,7 @@
 // kernels instantiate.  It lets tests/ check the field/curve/hash FORMULAS against the oracle on a
 // CPU-only box.  It is not part of the product: the product library has no CPU path, and nothing
 // outside tests/ builds or loads this file.
+#define SB_COUNT_WIDE 1
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -259,4 +260,11 @@ API uint64_t hs_fp6_cofactor_norm(const uint64_t* d, uint64_t* c) {
     fp6_cofactor_norm(&dd, &cc, &n);
     st6(c, cc);
     return n;
+}
+
+// 32x32->64 multiplies executed since the last call (cost figures of DESIGN.md; test-only counter in fp.cuh)
+API unsigned long long hs_wide_count_reset() {
+    unsigned long long v = g_wide_count;
+    g_wide_count = 0;
+    return v;
 }

@@ -416,3 +416,23 @@ def test_fp_denominator_jacobian_operations(hostsim):
         assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), NOP, p(out)) == 0 and pt_from96(out) == a
     t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
     assert hostsim.hs_jf_dbl(p(pt_to96(t2)), C.c_uint64(5), p(out)) == 1
+
+
+def test_executed_multiply_counts_match_design_doc(hostsim):
+    """The executed 32x32->64 multiply counts quoted in DESIGN.md §4 (test-only counter in the host build)."""
+    hostsim.hs_wide_count_reset.restype = C.c_ulonglong
+    w = make_workload(91, 2, lens=[8, 8])
+    used = C.c_int(0)
+    counts = {}
+    for name, fn in (("fast", lambda i, mb, m: hostsim.hs_verify_one_fast(p(w["sigs"][i].copy()), p(w["pk"][i].copy()), 0, p(mb),
+                                                                         C.c_uint64(len(m)), C.byref(used))),
+                     ("exact", lambda i, mb, m: hostsim.hs_verify_one(p(w["sigs"][i].copy()), p(w["pk"][i].copy()), 0, p(mb),
+                                                                      C.c_uint64(len(m))))):
+        hostsim.hs_gtab()
+        hostsim.hs_wide_count_reset()
+        mb = np.frombuffer(w["msgs"][0], dtype=np.uint8).copy()
+        assert fn(0, mb, w["msgs"][0]) == 0
+        counts[name] = hostsim.hs_wide_count_reset()
+    assert 300_000 < counts["fast"] < 380_000, counts       # DESIGN.md: ~0.34 M multiplies per verification
+    assert 500_000 < counts["exact"] < 560_000, counts      # DESIGN.md: ~0.53 M (exact Jacobian kernel)
+    print(counts)
