@@ -252,23 +252,22 @@ SB_SCALE_FN fp6 fp6_scale_diff(fp6 a, fp_t s, fp6 b, fp_t t) {
 
 // p <- 2 p.  Returns true on the exceptional input (a point of order 2: the result would be the identity).
 SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
-    fp6 X = p->X, Y = p->Y;
-    fp_t w = p->w;
-    fp6 d = fp6_dbl(Y), c;
-    fp_t n;
-    fp6_cofactor_norm(&d, &c, &n);
+    fp6 X = p->X, Y = p->Y, c;
+    fp_t w = p->w, n;
+    fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / m,  m = 2 n
+    fp_t m = fp_add(n, n);
     fp_t w4 = fp_sqr(fp_sqr_nc(w));
     fp6 xx = fp6_sqr(X);
     fp6 num = fp6_add(fp6_dbl(xx), xx);
     num.c[0] = fp_add(num.c[0], w4);        // 3 X^2 + a w^4, a = 1
-    fp6 L = fp6_mul(num, c);                // slope = L / (n w)
-    fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
-    fp6 A = fp6_scale(X, n2);
+    fp6 L = fp6_mul(num, c);                // slope = L / (m w)
+    fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
+    fp6 A = fp6_scale(X, m2);
     fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
-    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, n3));
+    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
     p->X = X3;
     p->Y = Y3;
-    p->w = fp_mul(n, w);
+    p->w = fp_mul(m, w);
     return n == 0;
 }
 
@@ -372,6 +371,10 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     //   q (odd digits 2k+1):  [q]P = 2 O_1 + R_0        h (digits m = k+1):  h*P = O_0
     jf_pt Rq = Bq[7], Oq = Bq[7], Rh = Bh[7], Oh = Bh[7];
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
+    // `same_h`: O_h and R_h are the same (finite) point.  It happens whenever the buckets below the highest used
+    // digit magnitude are empty (~2e-4 of random challenges): O += R is then a doubling, taken on a divergent
+    // branch by those few threads instead of being handed to the exact kernel.
+    bool same_h = !eRh;
 #pragma unroll 1
     for (int b = 6; b >= 0; b--) {
         SB_PHASE_SYNC(1);
@@ -384,8 +387,15 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
         }
         eb = !((h_seen >> b) & 1);
         exc |= jf_add(&Rh, &Bh[b], jf_add_mode(eRh, eb, false));
+        if (!eb && !eRh) same_h = false;  // a real addition changed R
         eRh = eRh && eb;
-        exc |= jf_add(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
+        if (__builtin_expect(same_h && !eOh, 0)) {
+            exc |= jf_dbl(&Oh);           // O == R: O + R = 2 O
+            same_h = false;
+        } else {
+            exc |= jf_add(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
+            same_h = eOh && !eRh;         // O was empty and has just been set to R
+        }
         eOh = eOh && eRh;
     }
     if (eOq || eRq) exc = true;  // degenerate digit pattern: leave it to the exact routine
