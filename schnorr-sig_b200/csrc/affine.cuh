@@ -302,7 +302,8 @@ SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
     fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), B);
     fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));   // ... - y1 w3^3
     fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
-    bool active = mode == JOP_ADD || mode == JOP_SUB;
+    bool wanted = mode == JOP_ADD || mode == JOP_SUB;
+    bool active = wanted && n != 0;  // on the exceptional input acc is left untouched
     bool set = mode == JOP_SET || mode == JOP_SETNEG;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -310,7 +311,20 @@ SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
         acc->Y.c[i] = active ? Y3.c[i] : (set ? Y2.c[i] : Y1.c[i]);
     }
     acc->w = active ? w3 : (set ? w2 : w1);
-    return active && n == 0;
+    return wanted && n == 0;
+}
+
+// Exact accumulation for the Pippenger buckets (batch.cuh): acc += (+|-) t with t affine (t->w == 1).
+// The identity is w == 0; P + P and P - P (repeated signers put equal points into one bucket,
+// src/batch.rs:167-169) are resolved on a rarely taken branch.
+SB_DEV void jf_madd_exact(jf_pt* acc, const jf_pt* t, bool neg) {
+    bool exc = jf_add(acc, t, jf_add_mode(acc->w == 0, false, neg));
+    if (__builtin_expect(exc, 0)) {
+        fp_t w = acc->w;
+        fp6 ty = fp6_scale(neg ? fp6_neg(t->Y) : t->Y, fp_mul_nc(fp_sqr_nc(w), w));
+        bool same = fp6_eq(acc->Y, ty);
+        if (!same || jf_dbl(acc)) acc->w = 0;  // P - P, or the doubling of a 2-torsion point
+    }
 }
 
 // a == b as points (both finite)

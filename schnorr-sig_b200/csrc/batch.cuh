@@ -221,6 +221,11 @@ __device__ __forceinline__ size_t bucket_of_slot(const msm_plan& pl, uint32_t sl
     uint32_t k = slot / (uint32_t)(pl.B + 1), b = slot % (uint32_t)(pl.B + 1);
     return (size_t)k * pl.B + (b - 1);
 }
+__device__ __forceinline__ void store_jf_as_jac(jac_pt* out, const jf_pt& p) {
+    out->X = p.X;
+    out->Y = p.Y;
+    out->Z = fp6{{p.w, 0, 0, 0, 0, 0}};
+}
 __global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restrict__ pts, msm_plan pl, uint32_t nslots,
                                                          uint32_t T, const uint32_t* __restrict__ offsets,
                                                          const uint32_t* __restrict__ counts,
@@ -240,22 +245,30 @@ __global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restr
         if (offsets[m] <= lo) a = m; else b = m;
     }
     uint32_t s = a, beg_s = offsets[s], end_s = beg_s + counts[s];
-    jac_pt acc = jac_identity();
+    // the running bucket sum lives in (X, Y, w) coordinates with w in Fp (affine.cuh): an addition of an affine point
+    // is 2M + 1S + cofactor + scalings instead of the 7M + 4S of a Jacobian mixed addition; (X, Y, w) IS a Jacobian
+    // point with Z = w, which is how the later stages read it (identity: w = 0)
+    jf_pt acc, tp;
+    acc.X = fp6_one();
+    acc.Y = fp6_one();
+    acc.w = 0;
+    tp.w = 1;
     for (uint32_t pos = lo; pos < hi; pos++) {
         if (pos >= end_s) {
             // flush bucket s (it ended inside this segment) and move to the bucket holding pos
-            if (beg_s >= lo) buckets[bucket_of_slot(pl, s)] = acc;          // complete: began and ended here
-            else { parts[2 * t + 0].pt = acc; parts[2 * t + 0].slot = (int32_t)s; }   // head partial
-            acc = jac_identity();
+            if (beg_s >= lo) store_jf_as_jac(&buckets[bucket_of_slot(pl, s)], acc);          // complete: began and ended here
+            else { store_jf_as_jac(&parts[2 * t + 0].pt, acc); parts[2 * t + 0].slot = (int32_t)s; }   // head partial
+            acc.w = 0;
             do { s++; beg_s = offsets[s]; end_s = beg_s + counts[s]; } while (pos >= end_s);
         }
         uint32_t v = sorted[pos];
-        jac_madd_mem(&acc, pts + (size_t)(v & 0x7fffffffu) * 12, (v >> 31) != 0, false);
+        load_affine(pts, v & 0x7fffffffu, tp.X, tp.Y);
+        jf_madd_exact(&acc, &tp, (v >> 31) != 0);
     }
     bool began_here = beg_s >= lo, ends_here = end_s <= hi;
-    if (began_here && ends_here) buckets[bucket_of_slot(pl, s)] = acc;
-    else if (!began_here) { parts[2 * t + 0].pt = acc; parts[2 * t + 0].slot = (int32_t)s; }   // head (maybe whole segment)
-    else { parts[2 * t + 1].pt = acc; parts[2 * t + 1].slot = (int32_t)s; }                     // tail
+    if (began_here && ends_here) store_jf_as_jac(&buckets[bucket_of_slot(pl, s)], acc);
+    else if (!began_here) { store_jf_as_jac(&parts[2 * t + 0].pt, acc); parts[2 * t + 0].slot = (int32_t)s; }   // head (maybe whole segment)
+    else { store_jf_as_jac(&parts[2 * t + 1].pt, acc); parts[2 * t + 1].slot = (int32_t)s; }                     // tail
 }
 // one thread per slot: buckets that straddle segment boundaries are the sum of their partials
 __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t nslots, uint32_t T,

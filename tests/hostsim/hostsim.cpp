@@ -268,3 +268,12 @@ API unsigned long long hs_wide_count_reset() {
     g_wide_count = 0;
     return v;
 }
+// Pippenger bucket accumulation step: acc (affine, or identity when a_inf) scrambled by wa, += (+|-) b; returns the
+// affine result (out_inf = identity)
+API void hs_jf_madd_exact(const uint8_t* a96, int a_inf, uint64_t wa, const uint8_t* b96, int neg, uint8_t* out96, int* out_inf) {
+    jf_pt a = jf_from_affine(a96, wa), t = jf_from_affine(b96, 1);
+    if (a_inf) a.w = 0;
+    jf_madd_exact(&a, &t, neg != 0);
+    *out_inf = a.w == 0;
+    if (a.w != 0) jf_to_affine(a, out96);
+}

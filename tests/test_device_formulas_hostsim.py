@@ -433,3 +433,28 @@ def test_executed_multiply_counts_match_design_doc(hostsim):
     assert 300_000 < counts["fast"] < 380_000, counts       # ~0.34 M multiplies per verification
     assert 500_000 < counts["exact"] < 560_000, counts      # ~0.53 M (exact Jacobian kernel)
     print(counts)
+
+
+def test_exact_bucket_accumulation_step(hostsim):
+    """jf_madd_exact (MSM bucket accumulation): identity accumulator, P + P, P - P, 2-torsion, generic."""
+    rng = np.random.default_rng(43)
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 3)] + [kat]
+    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+
+    def run(a, b, neg, w=0x1234567):
+        A = pt_to96(a) if a is not o.INF else np.zeros(96, dtype=np.uint8)
+        hostsim.hs_jf_madd_exact(p(A), int(a is o.INF), C.c_uint64(w), p(pt_to96(b)), int(neg), p(out), C.byref(oi))
+        return o.INF if oi.value else pt_from96(out)
+
+    for a in pts:
+        for b in pts:
+            for neg in (False, True):
+                want = o.pt_add(a, o.pt_neg(b) if neg else b)
+                assert run(a, b, neg) == want
+        assert run(o.INF, a, False) == a and run(o.INF, a, True) == o.pt_neg(a)
+        assert run(a, a, False, w=1) == o.pt_add(a, a) and run(a, a, True, w=o.P - 1) is o.INF
+    assert run(t2, t2, False) is o.INF and run(t2, t2, True) is o.INF
