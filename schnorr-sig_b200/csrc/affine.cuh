@@ -334,6 +334,22 @@ SB_DEV bool jf_eq_neg(const jf_pt& a, const jf_pt& b, bool& x_eq) {
     return x_eq && fp6_eq(fp6_scale(a.Y, fp_mul_nc(wbs, b.w)), fp6_neg(fp6_scale(b.Y, fp_mul_nc(was, a.w))));
 }
 
+// General exact addition acc += src of two (X, Y, w) points, either of which may be the identity (w == 0).
+SB_DEV void jf_add_exact(jf_pt* acc, const jf_pt* src) {
+    bool exc = jf_add(acc, src, jf_add_mode(acc->w == 0, src->w == 0, false));
+    if (__builtin_expect(exc, 0)) {
+        // x(acc) == x(src):  Y1 w2^3 == Y2 w1^3  <=>  the same point (doubling), otherwise opposite points
+        fp_t w1 = acc->w, w2 = src->w;
+        fp6 a = fp6_scale(acc->Y, fp_mul_nc(fp_sqr_nc(w2), w2)), b = fp6_scale(src->Y, fp_mul_nc(fp_sqr_nc(w1), w1));
+        if (!fp6_eq(a, b) || jf_dbl(acc)) acc->w = 0;
+    }
+}
+// acc <- 2 acc, exact (identity and 2-torsion points give the identity)
+SB_DEV void jf_dbl_exact(jf_pt* acc) {
+    if (acc->w == 0) return;
+    if (jf_dbl(acc)) acc->w = 0;
+}
+
 enum fast_result : int {
     FAST_TORSION_FREE = 0,      // [q]P == O, h*P + e*G computed
     FAST_NOT_TORSION_FREE = 1,  // [q]P != O

@@ -221,11 +221,21 @@ __device__ __forceinline__ size_t bucket_of_slot(const msm_plan& pl, uint32_t sl
     uint32_t k = slot / (uint32_t)(pl.B + 1), b = slot % (uint32_t)(pl.B + 1);
     return (size_t)k * pl.B + (b - 1);
 }
+// (X, Y, w) is a Jacobian point with Z = w in Fp: the arrays between the MSM stages hold jac_pt records whose Z has
+// only its first coefficient set (identity: w = 0)
 __device__ __forceinline__ void store_jf_as_jac(jac_pt* out, const jf_pt& p) {
     out->X = p.X;
     out->Y = p.Y;
     out->Z = fp6{{p.w, 0, 0, 0, 0, 0}};
 }
+__device__ __forceinline__ jf_pt load_jac_as_jf(const jac_pt* in) {
+    jf_pt r;
+    r.X = in->X;
+    r.Y = in->Y;
+    r.w = in->Z.c[0];
+    return r;
+}
+__device__ __forceinline__ jf_pt jf_identity() { return jf_pt{fp6_one(), fp6_one(), 0}; }
 __global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restrict__ pts, msm_plan pl, uint32_t nslots,
                                                          uint32_t T, const uint32_t* __restrict__ offsets,
                                                          const uint32_t* __restrict__ counts,
@@ -282,24 +292,27 @@ __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t
     uint32_t beg = offsets[s], end = beg + cnt;
     uint32_t sa = beg / T, sb = (end - 1) / T;
     if (sa == sb) return;  // written directly by its segment
-    jac_pt acc = jac_identity();
+    jf_pt acc = jf_identity();
     for (uint32_t g = sa; g <= sb; g++) {
 #pragma unroll 1
         for (int w = 0; w < 2; w++) {
             const seg_partial* p = &parts[2 * (size_t)g + w];
-            if (p->slot == (int32_t)s) jac_add_mem(&acc, &p->pt, false);
+            if (p->slot == (int32_t)s) {
+                jf_pt t = load_jac_as_jf(&p->pt);
+                jf_add_exact(&acc, &t);
+            }
         }
     }
-    buckets[bucket_of_slot(pl, s)] = acc;
+    store_jf_as_jac(&buckets[bucket_of_slot(pl, s)], acc);
 }
 
 // small multiple m * P (m >= 1) by double-and-add from the top set bit
-__device__ void jac_mul_small_mem(jac_pt* out, const jac_pt* P, uint32_t m) {
-    jac_pt acc = *P;
+__device__ void jf_mul_small(jf_pt* out, const jf_pt* P, uint32_t m) {
+    jf_pt acc = *P;
 #pragma unroll 1
     for (int bit = 30 - __clz(m); bit >= 0; bit--) {
-        jac_dbl_mem(&acc);
-        if ((m >> bit) & 1) jac_add_mem(&acc, P, false);
+        jf_dbl_exact(&acc);
+        if ((m >> bit) & 1) jf_add_exact(&acc, P);
     }
     *out = acc;
 }
@@ -313,42 +326,46 @@ __global__ void __launch_bounds__(64) k_msm_window_sum(msm_plan pl, const jac_pt
     int k = t / pl.chunks, ch = t % pl.chunks;
     int lo = ch * pl.chunk_sz + 1;
     const jac_pt* bk = buckets + (size_t)k * pl.B + (lo - 1);
-    jac_pt running = jac_identity(), acc = jac_identity();
+    jf_pt running = jf_identity(), acc = jf_identity();
 #pragma unroll 1
     for (int b = pl.chunk_sz - 1; b >= 0; b--) {
-        jac_add_mem(&running, &bk[b], false);
-        jac_add_mem(&acc, &running, false);
+        jf_pt bb = load_jac_as_jf(&bk[b]);
+        jf_add_exact(&running, &bb);
+        jf_add_exact(&acc, &running);
     }
     if (lo > 1) {
-        jac_pt m;
-        jac_mul_small_mem(&m, &running, (uint32_t)(lo - 1));
-        jac_add_mem(&acc, &m, false);
+        jf_pt m;
+        jf_mul_small(&m, &running, (uint32_t)(lo - 1));
+        jf_add_exact(&acc, &m);
     }
-    chunk_out[t] = acc;
+    store_jf_as_jac(&chunk_out[t], acc);
 }
 // one warp per window: lanes add strided chunk results, then a shuffle tree ("warp-shuffle bucket reduction")
-__device__ __forceinline__ jac_pt shfl_down_jac(const jac_pt& p, int delta) {
-    jac_pt r;
+__device__ __forceinline__ jf_pt shfl_down_jf(const jf_pt& p, int delta) {
+    jf_pt r;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
         r.X.c[c] = __shfl_down_sync(0xffffffffu, p.X.c[c], delta);
         r.Y.c[c] = __shfl_down_sync(0xffffffffu, p.Y.c[c], delta);
-        r.Z.c[c] = __shfl_down_sync(0xffffffffu, p.Z.c[c], delta);
     }
+    r.w = __shfl_down_sync(0xffffffffu, p.w, delta);
     return r;
 }
 __global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out,
                                                         jac_pt* __restrict__ windows) {
     int k = blockIdx.x, lane = threadIdx.x;
-    jac_pt acc = jac_identity();
+    jf_pt acc = jf_identity();
 #pragma unroll 1
-    for (int ch = lane; ch < pl.chunks; ch += 32) jac_add_mem(&acc, &chunk_out[(size_t)k * pl.chunks + ch], false);
+    for (int ch = lane; ch < pl.chunks; ch += 32) {
+        jf_pt t = load_jac_as_jf(&chunk_out[(size_t)k * pl.chunks + ch]);
+        jf_add_exact(&acc, &t);
+    }
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
-        jac_pt o = shfl_down_jac(acc, d);
-        jac_add_mem(&acc, &o, false);
+        jf_pt o = shfl_down_jf(acc, d);
+        jf_add_exact(&acc, &o);
     }
-    if (lane == 0) windows[k] = acc;
+    if (lane == 0) store_jf_as_jac(&windows[k], acc);
 }
 // Horner over the windows is a serial chain of ~255 doublings.  Four lanes of one warp share each
 // doubling: the eight squarings of dbl-2007-bl are issued as two rounds of independent squarings on

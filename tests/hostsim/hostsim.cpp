@@ -277,3 +277,11 @@ API void hs_jf_madd_exact(const uint8_t* a96, int a_inf, uint64_t wa, const uint
     *out_inf = a.w == 0;
     if (a.w != 0) jf_to_affine(a, out96);
 }
+API void hs_jf_add_exact(const uint8_t* a96, int a_inf, uint64_t wa, const uint8_t* b96, int b_inf, uint64_t wb, uint8_t* out96, int* out_inf) {
+    jf_pt a = jf_from_affine(a96, wa), b = jf_from_affine(b96, wb);
+    if (a_inf) a.w = 0;
+    if (b_inf) b.w = 0;
+    jf_add_exact(&a, &b);
+    *out_inf = a.w == 0;
+    if (a.w != 0) jf_to_affine(a, out96);
+}

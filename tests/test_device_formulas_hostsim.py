@@ -458,3 +458,28 @@ def test_exact_bucket_accumulation_step(hostsim):
         assert run(o.INF, a, False) == a and run(o.INF, a, True) == o.pt_neg(a)
         assert run(a, a, False, w=1) == o.pt_add(a, a) and run(a, a, True, w=o.P - 1) is o.INF
     assert run(t2, t2, False) is o.INF and run(t2, t2, True) is o.INF
+
+
+def test_exact_general_addition_in_fp_denominator_coordinates(hostsim):
+    """jf_add_exact (MSM reduction stages): identity operands, P + P, P - P, generic, for scrambled denominators."""
+    rng = np.random.default_rng(44)
+    G = o.generator()
+    kat = (o.KAT_X, o.KAT_Y)
+    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 3)] + [kat, o.INF]
+    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
+    out = np.zeros(96, dtype=np.uint8)
+    oi = C.c_int(0)
+    z96 = np.zeros(96, dtype=np.uint8)
+
+    def run(a, b, wa=0x1234567, wb=0xfedcba987):
+        A = pt_to96(a) if a is not o.INF else z96
+        B = pt_to96(b) if b is not o.INF else z96
+        hostsim.hs_jf_add_exact(p(A), int(a is o.INF), C.c_uint64(wa), p(B), int(b is o.INF), C.c_uint64(wb), p(out), C.byref(oi))
+        return o.INF if oi.value else pt_from96(out)
+
+    for a in pts:
+        for b in pts:
+            assert run(a, b) == o.pt_add(a, b)
+        if a is not o.INF:
+            assert run(a, o.pt_neg(a)) is o.INF and run(a, a, 3, 5) == o.pt_add(a, a)
+    assert run(t2, t2) is o.INF
