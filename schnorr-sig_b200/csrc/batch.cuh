@@ -367,47 +367,72 @@ __global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_p
     }
     if (lane == 0) store_jf_as_jac(&windows[k], acc);
 }
-// Horner over the windows is a serial chain of ~255 doublings.  Four lanes of one warp share each
-// doubling: the eight squarings of dbl-2007-bl are issued as two rounds of independent squarings on
-// different lanes (SIMT: one instruction stream, lane-dependent operands), the results are exchanged with
-// warp shuffles, and the cheap linear parts are computed redundantly -> 4 field-op levels instead of 9.
-__device__ __forceinline__ fp6 shfl_fp6(const fp6& a, int src) {
+// Horner over the windows is a serial chain of ~255 doublings, i.e. pure latency.  24 lanes of one warp share each
+// doubling on two levels:
+//  * an Fp6 value is DISTRIBUTED over a group of six lanes, lane k holding coefficient k; a product is then one
+//    coefficient per lane (six 64x64 products + one reduction), the operands travelling by warp shuffles
+//    (the source lane pre-selects b_j or 7 b_j for the wrap-around terms, so 12 x 64-bit shuffles per product);
+//  * four such groups run the independent squarings of dbl-2007-bl side by side (two rounds), the linear parts
+//    are coefficient-wise and computed redundantly by every group -> 4 short product rounds instead of 9 products.
+static constexpr unsigned HORNER_MASK = 0x00ffffffu;  // lanes 0..23 = 4 groups x 6 coefficients
+__device__ __forceinline__ fp_t shfl_fp(fp_t v, int src) { return __shfl_sync(HORNER_MASK, v, src); }
+// coefficient k (of the lane) of a * b; a, b = the lane's own coefficients of the two operands of ITS group
+__device__ __noinline__ fp_t dfp6_mul(fp_t a, fp_t b, int k, int gbase) {
+    fp_t b7 = fp_mul7_nc(b);
+    wide_acc w;
+    wide_zero(w);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        // step i: lane k needs a_i and b'_(k - i mod 6); source lane j is read by lane (j + i) mod 6, which wraps iff j + i >= 6
+        fp_t send = (k + i >= 6) ? b7 : b;
+        int j = k - i;
+        j += j < 0 ? 6 : 0;
+        wide_mac(w, shfl_fp(a, gbase + i), shfl_fp(send, gbase + j));
+    }
+    return wide_reduce(w);
+}
+// one doubling of the point whose coefficients (x, y, z of lane k) are replicated over the four groups
+__device__ void jac_dbl_dist(fp_t& x, fp_t& y, fp_t& z, int g, int k) {
+    int gbase = 6 * g;
+    fp_t yz = fp_add(y, z);
+    fp_t op1 = g == 0 ? x : (g == 1 ? y : (g == 2 ? z : yz));
+    fp_t s1 = dfp6_mul(op1, op1, k, gbase);
+    fp_t XX = shfl_fp(s1, k), YY = shfl_fp(s1, 6 + k), ZZ = shfl_fp(s1, 12 + k), W = shfl_fp(s1, 18 + k);
+    fp_t op2 = g == 0 ? fp_add(x, YY) : (g == 1 ? YY : ZZ);
+    fp_t s2 = dfp6_mul(op2, op2, k, gbase);
+    fp_t t = shfl_fp(s2, k), YYYY = shfl_fp(s2, 6 + k), Z4 = shfl_fp(s2, 12 + k);
+    fp_t S = fp_dbl(fp_sub(fp_sub(t, XX), YYYY));
+    fp_t M = fp_add(fp_add(fp_dbl(XX), XX), Z4);  // 3 XX + a ZZ^2, a = 1
+    fp_t X3 = fp_sub(dfp6_mul(M, M, k, gbase), fp_dbl(S));
+    fp_t Y3 = fp_sub(dfp6_mul(M, fp_sub(S, X3), k, gbase), fp_dbl(fp_dbl(fp_dbl(YYYY))));
+    z = fp_sub(fp_sub(W, YY), ZZ);
+    x = X3;
+    y = Y3;
+}
+// all coefficients of a distributed value, gathered from group 0
+__device__ __forceinline__ fp6 gather_fp6(fp_t v) {
     fp6 r;
 #pragma unroll
-    for (int c = 0; c < 6; c++) r.c[c] = __shfl_sync(0xfu, a.c[c], src);
+    for (int c = 0; c < 6; c++) r.c[c] = shfl_fp(v, c);
     return r;
-}
-__device__ __forceinline__ fp6 pick4(int lane, const fp6& a, const fp6& b, const fp6& c, const fp6& d) {
-    fp6 r;
-#pragma unroll
-    for (int k = 0; k < 6; k++) r.c[k] = lane == 0 ? a.c[k] : (lane == 1 ? b.c[k] : (lane == 2 ? c.c[k] : d.c[k]));
-    return r;
-}
-__device__ void jac_dbl_coop4(jac_pt& p, int lane) {  // lanes 0..3 hold identical copies of p on entry and exit
-    fp6 s1 = fp6_sqr(pick4(lane, p.X, p.Y, p.Z, fp6_add(p.Y, p.Z)));
-    fp6 XX = shfl_fp6(s1, 0), YY = shfl_fp6(s1, 1), ZZ = shfl_fp6(s1, 2), W = shfl_fp6(s1, 3);
-    fp6 s2 = fp6_sqr(pick4(lane, fp6_add(p.X, YY), YY, ZZ, ZZ));
-    fp6 t = shfl_fp6(s2, 0), YYYY = shfl_fp6(s2, 1), Z4 = shfl_fp6(s2, 2);
-    fp6 S = fp6_dbl(fp6_sub(fp6_sub(t, XX), YYYY));
-    fp6 M = fp6_add(fp6_add(fp6_dbl(XX), XX), Z4);
-    jac_pt r;
-    r.X = fp6_sub(fp6_sqr(M), fp6_dbl(S));
-    r.Y = fp6_sub(fp6_mul(M, fp6_sub(S, r.X)), fp6_dbl(fp6_dbl(fp6_dbl(YYYY))));
-    r.Z = fp6_sub(fp6_sub(W, YY), ZZ);
-    p = r;
 }
 // partial192 = Jacobian point (18 u64) || partial scalar sum (4 u64) || bad flag (u64) || pad
 __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, const jac_pt* __restrict__ windows,
                                                    const uint32_t* __restrict__ lin, const int* __restrict__ bad,
                                                    uint64_t* __restrict__ partial) {
     int lane = threadIdx.x;
-    if (blockIdx.x != 0 || lane >= 4) return;
-    jac_pt acc = windows[pl.K - 1];
+    if (blockIdx.x != 0 || lane >= 24) return;
+    int g = lane / 6, k = lane % 6;
+    jac_pt acc = windows[pl.K - 1];   // replicated on every lane between the doubling runs
 #pragma unroll 1
-    for (int k = pl.K - 2; k >= 0; k--) {
+    for (int w = pl.K - 2; w >= 0; w--) {
+        fp_t x = acc.X.c[k], y = acc.Y.c[k], z = acc.Z.c[k];
 #pragma unroll 1
-        for (int s = 0; s < pl.c; s++) jac_dbl_coop4(acc, lane);
-        jac_add_mem(&acc, &windows[k], false);  // all four lanes redundantly
+        for (int s = 0; s < pl.c; s++) jac_dbl_dist(x, y, z, g, k);
+        acc.X = gather_fp6(x);
+        acc.Y = gather_fp6(y);
+        acc.Z = gather_fp6(z);
+        jac_add_mem(&acc, &windows[w], false);  // all lanes redundantly (exceptional cases included)
     }
     if (lane != 0) return;
 #pragma unroll
