@@ -376,35 +376,21 @@ __global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_p
 //    are coefficient-wise and computed redundantly by every group -> 4 short product rounds instead of 9 products.
 static constexpr unsigned HORNER_MASK = 0x00ffffffu;  // lanes 0..23 = 4 groups x 6 coefficients
 __device__ __forceinline__ fp_t shfl_fp(fp_t v, int src) { return __shfl_sync(HORNER_MASK, v, src); }
-// coefficient k (of the lane) of a * b; a, b = the lane's own coefficients of the two operands of ITS group
-__device__ __noinline__ fp_t dfp6_mul(fp_t a, fp_t b, int k, int gbase) {
-    fp_t b7 = fp_mul7_nc(b);
-    wide_acc w;
-    wide_zero(w);
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        // step i: lane k needs a_i and b'_(k - i mod 6); source lane j is read by lane (j + i) mod 6, which wraps iff j + i >= 6
-        fp_t send = (k + i >= 6) ? b7 : b;
-        int j = k - i;
-        j += j < 0 ? 6 : 0;
-        wide_mac(w, shfl_fp(a, gbase + i), shfl_fp(send, gbase + j));
-    }
-    return wide_reduce(w);
-}
+// (the six-lane product dfp6_mul lives in dist.cuh)
 // one doubling of the point whose coefficients (x, y, z of lane k) are replicated over the four groups
 __device__ void jac_dbl_dist(fp_t& x, fp_t& y, fp_t& z, int g, int k) {
     int gbase = 6 * g;
     fp_t yz = fp_add(y, z);
     fp_t op1 = g == 0 ? x : (g == 1 ? y : (g == 2 ? z : yz));
-    fp_t s1 = dfp6_mul(op1, op1, k, gbase);
+    fp_t s1 = dfp6_mul(HORNER_MASK, op1, op1, k, gbase);
     fp_t XX = shfl_fp(s1, k), YY = shfl_fp(s1, 6 + k), ZZ = shfl_fp(s1, 12 + k), W = shfl_fp(s1, 18 + k);
     fp_t op2 = g == 0 ? fp_add(x, YY) : (g == 1 ? YY : ZZ);
-    fp_t s2 = dfp6_mul(op2, op2, k, gbase);
+    fp_t s2 = dfp6_mul(HORNER_MASK, op2, op2, k, gbase);
     fp_t t = shfl_fp(s2, k), YYYY = shfl_fp(s2, 6 + k), Z4 = shfl_fp(s2, 12 + k);
     fp_t S = fp_dbl(fp_sub(fp_sub(t, XX), YYYY));
     fp_t M = fp_add(fp_add(fp_dbl(XX), XX), Z4);  // 3 XX + a ZZ^2, a = 1
-    fp_t X3 = fp_sub(dfp6_mul(M, M, k, gbase), fp_dbl(S));
-    fp_t Y3 = fp_sub(dfp6_mul(M, fp_sub(S, X3), k, gbase), fp_dbl(fp_dbl(fp_dbl(YYYY))));
+    fp_t X3 = fp_sub(dfp6_mul(HORNER_MASK, M, M, k, gbase), fp_dbl(S));
+    fp_t Y3 = fp_sub(dfp6_mul(HORNER_MASK, M, fp_sub(S, X3), k, gbase), fp_dbl(fp_dbl(fp_dbl(YYYY))));
     z = fp_sub(fp_sub(W, YY), ZZ);
     x = X3;
     y = Y3;

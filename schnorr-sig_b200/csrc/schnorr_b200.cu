@@ -20,6 +20,7 @@
 #include "../../include/cheetah_params.h"
 #include "../../include/schnorr_b200.h"
 #include "verify.cuh"
+#include "dist.cuh"
 
 using namespace sb;
 
@@ -43,6 +44,7 @@ struct schnorr_b200_ctx {
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
     bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the affine fast path (A/B measurements, tests)
+    size_t dist_max = 8192;                         // calls up to this many signatures use the six-lanes-per-signature kernel
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
@@ -245,6 +247,59 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
     uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
     verdicts[i] = v;
     if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
+}
+
+// K2 for small calls: one signature per group of six lanes (dist.cuh), five signatures per warp.  Same verdicts and
+// the same hand-back list as k_verify_fast.
+static constexpr int DIST_THREADS = 128;
+static constexpr int DIST_SIGS_PER_BLOCK = (DIST_THREADS / 32) * 5;
+__global__ void __launch_bounds__(DIST_THREADS) k_verify_dist(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                              const uint64_t* __restrict__ msg_off,
+                                                              const uint64_t* __restrict__ gtab,
+                                                              uint8_t* __restrict__ verdicts,
+                                                              uint32_t* __restrict__ work_list,
+                                                              uint32_t* __restrict__ work_count) {
+    __shared__ uint32_t s_mds2[24];  // the circulant MDS row twice: M[i][j] = s_mds2[j - i + 12]
+    if (threadIdx.x < 24) s_mds2[threadIdx.x] = c_mds_row[threadIdx.x % 12];
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g = lane / 6, k = lane % 6;
+    if (g >= 5) return;  // lanes 30, 31 idle
+    size_t i = ((size_t)blockIdx.x * (DIST_THREADS / 32) + warp) * 5 + g;
+    if (i >= in.n) return;
+    int gbase = 6 * g;
+    unsigned mask = 0x3fu << gbase;
+    uint8_t fl = in.flags[i];
+    if (fl & FL_MALFORMED) {
+        if (k == 0) verdicts[i] = VERDICT_MALFORMED;
+        return;
+    }
+    uint8_t v;
+    if (fl & FL_PK_INF) {
+        v = VERDICT_NEEDS_EXACT;
+    } else {
+        bool x_ok = !(fl & FL_X_BAD);
+        // the lane's coefficient k of an Fp6 held in planes p0..p0+2 (ulonglong2 = two coefficients)
+        const uint64_t* pl = reinterpret_cast<const uint64_t*>(in.planes);
+        size_t n = in.n;
+        fp_t sx = pl[((size_t)(0 + (k >> 1)) * n + i) * 2 + (k & 1)];
+        fp_t px = pl[((size_t)(5 + (k >> 1)) * n + i) * 2 + (k & 1)];
+        fp_t py = pl[((size_t)(8 + (k >> 1)) * n + i) * 2 + (k & 1)];
+        scalar e = load_scalar_planes(in.planes, 3, n, i);
+        uint64_t off = msg_off[i];
+        scalar h = sc_zero();
+        if (x_ok) h = dchallenge_scalar(mask, sx, px, py, msgs + off, msg_off[i + 1] - off, k, gbase, s_mds2);
+        dpt r;
+        int fr = dverify_core(mask, px, py, h, e, gtab, &r, k, gbase);
+        bool eq = dall(mask, gbase, r.X == fp_mul(sx, fp_sqr_nc(r.w)));  // x(R) == sig.x  <=>  X == sig.x w^2
+        v = fr == FAST_EXCEPTIONAL ? VERDICT_NEEDS_EXACT
+            : (fr == FAST_NOT_TORSION_FREE ? VERDICT_INVALID_PUBLIC_KEY
+               : (!x_ok ? VERDICT_MALFORMED : (eq ? VERDICT_OK : VERDICT_INVALID_SIGNATURE)));
+    }
+    if (k == 0) {
+        verdicts[i] = v;
+        if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,7 +584,11 @@ static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint
     uint32_t* list = counters + schnorr_b200_ctx::MAX_CHUNKS + list_base;
     CUDA_TRY(ctx, cudaMemsetAsync(counters + counter, 0, 4, st));
     if (counter + 1 > ctx->exact_counters_used) ctx->exact_counters_used = counter + 1;
-    k_verify_fast<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+    if (soa.n <= ctx->dist_max)
+        k_verify_dist<<<grid_for(soa.n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list,
+                                                                                   counters + counter);
+    else
+        k_verify_fast<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
     // the exact kernel sizes itself from the device-side counter: blocks beyond it exit at once
     k_verify<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
     ctx->launches += 2;
@@ -568,6 +627,8 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     {
         const char* ex = getenv("SB_VERIFY_EXACT");
         ctx->exact_only = ex && ex[0] == '1';
+        const char* dm = getenv("SB_DIST_MAX");
+        if (dm) ctx->dist_max = (size_t)strtoull(dm, nullptr, 10);
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
@@ -640,6 +701,11 @@ int schnorr_b200_last_kernel_ms(schnorr_b200_ctx* ctx, float* ms) {
 int schnorr_b200_set_exact_only(schnorr_b200_ctx* ctx, int exact_only) {
     if (!ctx) return SCHNORR_B200_EARG;
     ctx->exact_only = exact_only != 0;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_set_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    ctx->dist_max = max_signatures;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {

@@ -88,6 +88,10 @@ class Engine:
         """True: every verification goes through the exact Jacobian kernel (A/B measurements, tests)."""
         self._check(self._L.schnorr_b200_set_exact_only(self._h, 1 if flag else 0), "set_exact_only")
 
+    def set_dist_threshold(self, max_signatures: int):
+        """Calls up to this many signatures use the six-lanes-per-signature kernel (0 = never, 2**62 = always)."""
+        self._check(self._L.schnorr_b200_set_dist_threshold(self._h, int(max_signatures)), "set_dist_threshold")
+
     def last_exact_count(self) -> int:
         """Items of the last verify_many* call that the affine fast path handed to the exact kernel."""
         c = C.c_uint64(0)

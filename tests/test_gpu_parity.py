@@ -156,6 +156,41 @@ def test_affine_fast_path_agrees_with_exact_kernel_and_hands_back_exceptional_it
     assert not (got_fast == 0xFF).any()
 
 
+@pytest.mark.parametrize("n", [1, 4, 5, 6, 21, 127, 1000])
+def test_warp_cooperative_kernel_matches_oracle(eng, n):
+    """k_verify_dist (one signature per six lanes, dist.cuh) forced for every size: ragged messages (different hash
+    trip counts inside one warp), injected faults, adversarial keys -> the oracle's verdicts."""
+    import schnorr_sig_b200 as s
+    rng = np.random.default_rng(900 + n)
+    lens = [int(x) for x in rng.integers(0, 60, n)]
+    lens[:min(n, 8)] = [0, 1, 6, 7, 8, 13, 14, 49][:min(n, 8)]
+    w = make_workload(900 + n, n, lens=lens)
+    w["n"], w["msg_len"] = n, 1
+    f = s.synth.inject_faults(w, every=7) if n >= 7 else dict(w, expect=np.zeros(n, np.uint8))
+    if n >= 21:
+        kat = (o.KAT_X, o.KAT_Y)
+        order = o.COFACTOR * o.Q
+        f["pk"][2] = pt_to96(o.pt_mul(kat, order // 2))
+        f["pk"][9] = pt_to96(o.pt_mul(kat, order // 29))
+        f["inf"][11] = 1
+        f["sigs"][13, 8:16] = 0xFF            # non-canonical sig.x limb
+        f["sigs"][15, 49:] = 0xFF             # e >= q
+    want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
+    eng.set_dist_threshold(2**62)
+    try:
+        got = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        handed_back = eng.last_exact_count()
+    finally:
+        eng.set_dist_threshold(8192)
+    assert np.array_equal(got, want)
+    assert handed_back <= (3 if n >= 21 else 0)
+    eng.set_dist_threshold(0)
+    try:
+        assert np.array_equal(eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"]), want)
+    finally:
+        eng.set_dist_threshold(8192)
+
+
 def test_verify_empty_and_argument_errors(eng):
     z = np.zeros((0, 81), np.uint8)
     assert eng.verify_many(z, np.zeros((0, 96), np.uint8), None, np.zeros(0, np.uint8), np.zeros(1, np.uint64)).size == 0

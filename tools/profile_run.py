@@ -63,6 +63,13 @@ def main():
                 timed("verify", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
                 assert int(d_out.max().item()) == 0
                 print("  handed to the exact kernel: %d of %d" % (eng.last_exact_count(), n), flush=True)
+            elif p == "verify_dist":
+                eng.set_dist_threshold(2**62)
+                timed("verify_dist", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
+                eng.set_dist_threshold(0)
+                assert int(d_out.max().item()) == 0
+                timed("verify_fast", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
+                eng.set_dist_threshold(8192)
             elif p == "verify_exact":
                 eng.set_exact_only(True)
                 timed("verify_exact", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
