@@ -68,7 +68,7 @@ int schnorr_b200_set_exact_only(schnorr_b200_ctx *ctx, int exact_only);
 int schnorr_b200_last_exact_count(schnorr_b200_ctx *ctx, uint64_t *count);
 /* Calls of at most `max_signatures` signatures (per pipeline chunk) run the warp-cooperative kernel (one signature per
  * six lanes: ~4x lower latency, 6x more parallelism per signature, ~1.5x the work); larger calls the one-signature-per-
- * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 8192; env SB_DIST_MAX overrides at creation. */
+ * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 10240 (measured crossover ~12 k); env SB_DIST_MAX overrides at creation. */
 int schnorr_b200_set_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
 
 /* hash_message(&Fp6, &PublicKey, &[u8]) -> [u8; 32]            src/signature.rs:274-306

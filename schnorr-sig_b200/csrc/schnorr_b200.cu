@@ -44,7 +44,7 @@ struct schnorr_b200_ctx {
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
     bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the affine fast path (A/B measurements, tests)
-    size_t dist_max = 8192;                         // calls up to this many signatures use the six-lanes-per-signature kernel
+    size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};

@@ -181,14 +181,14 @@ def test_warp_cooperative_kernel_matches_oracle(eng, n):
         got = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
         handed_back = eng.last_exact_count()
     finally:
-        eng.set_dist_threshold(8192)
+        eng.set_dist_threshold(10240)
     assert np.array_equal(got, want)
     assert handed_back <= (3 if n >= 21 else 0)
     eng.set_dist_threshold(0)
     try:
         assert np.array_equal(eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"]), want)
     finally:
-        eng.set_dist_threshold(8192)
+        eng.set_dist_threshold(10240)
 
 
 def test_verify_empty_and_argument_errors(eng):

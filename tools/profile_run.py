@@ -69,7 +69,7 @@ def main():
                 eng.set_dist_threshold(0)
                 assert int(d_out.max().item()) == 0
                 timed("verify_fast", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
-                eng.set_dist_threshold(8192)
+                eng.set_dist_threshold(10240)
             elif p == "verify_exact":
                 eng.set_exact_only(True)
                 timed("verify_exact", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
