@@ -22,29 +22,6 @@ struct aff_pt {
     fp6 x, y;
 };
 
-// ---- Fp3 squaring, 6 products -------------------------------------------------------------------
-SB_DEV fp3 fp3_sqr6(const fp3& a) {
-    fp_t a2_7 = fp_mul7_nc(a.c[2]);
-    fp3 r;
-    wide_acc w;
-    wide_zero(w);
-    wide_mac(w, a.c[1], a2_7);
-    wide_double(w);
-    wide_mac_sqr(w, a.c[0]);
-    r.c[0] = wide_reduce(w);
-    wide_zero(w);
-    wide_mac(w, a.c[0], a.c[1]);
-    wide_double(w);
-    wide_mac(w, a.c[2], a2_7);
-    r.c[1] = wide_reduce(w);
-    wide_zero(w);
-    wide_mac(w, a.c[0], a.c[2]);
-    wide_double(w);
-    wide_mac_sqr(w, a.c[1]);
-    r.c[2] = wide_reduce(w);
-    return r;
-}
-
 // adjugate and norm of d in Fp3 with lazily accumulated products (12 products, 4 reductions):
 //   d^-1 = (t0 + t1 v + t2 v^2) / n,   t0 = d0^2 - 7 d1 d2,  t1 = 7 d2^2 - d0 d1,  t2 = d1^2 - d0 d2,
 //   n = d0 t0 + 7 (d2 t1 + d1 t2)
@@ -209,6 +186,28 @@ struct jf_pt {
     fp_t w;
 };
 
+// a * b in Fp3 with the wrap-around multiples 7 b1, 7 b2 supplied by the caller (shared by several products)
+SB_DEV fp3 fp3_mul_pre(const fp3& a, const fp3& b, fp_t b7_1, fp_t b7_2) {
+    fp3 r;
+    wide_acc w;
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[0]);
+    wide_mac(w, a.c[1], b7_2);
+    wide_mac(w, a.c[2], b7_1);
+    r.c[0] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[1]);
+    wide_mac(w, a.c[1], b.c[0]);
+    wide_mac(w, a.c[2], b7_2);
+    r.c[1] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, a.c[0], b.c[2]);
+    wide_mac(w, a.c[1], b.c[1]);
+    wide_mac(w, a.c[2], b.c[0]);
+    r.c[2] = wide_reduce(w);
+    return r;
+}
+
 // d * c = n,  c in Fp6, n in Fp;  n == 0 <=> d == 0
 SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
     fp3 a0, a1, adj;
@@ -218,7 +217,8 @@ SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
     fp3 nn = fp3{{fp_sub(s0.c[0], fp_mul7(s1.c[2])), fp_sub(s0.c[1], s1.c[0]), fp_sub(s0.c[2], s1.c[1])}};
     fp3_adj_norm_lazy(nn, adj, *n);  // 1/N = adj / n
     fp3 na1 = fp3{{FP_P - a1.c[0], FP_P - a1.c[1], FP_P - a1.c[2]}};
-    *c = fp6_join(fp3_mul(a0, adj), fp3_mul(na1, adj));
+    fp_t adj7_1 = fp_mul7_nc(adj.c[1]), adj7_2 = fp_mul7_nc(adj.c[2]);
+    *c = fp6_join(fp3_mul_pre(a0, adj, adj7_1, adj7_2), fp3_mul_pre(na1, adj, adj7_1, adj7_2));
 }
 
 // a * s for s in Fp (any 64-bit representative)
