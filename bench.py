@@ -464,6 +464,27 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
                     "exchange": "one all_gather of 192 B per rank" if world > 1 else "none (1 GPU)"}
     if rank == 0 and (verdict != 0 or verdict_bad != 2):
         raise SystemExit("batch verification returned verdicts %r / %r (expected 0 / 2)" % (verdict, verdict_bad))
+    # small calls through the host API (the reference's own Criterion case is ONE verify, benches/schnorr.rs:60-77):
+    # host buffers in, verdicts out, wall clock around the call; rank 0 only
+    if rank == 0:
+        small = {}
+        for ns in (1, 1024):
+            hs = {k: hin[k] for k in ("sk", "nonce", "blob", "off")}
+            pk_s, inf_s = eng.keygen(hs["sk"][:ns])
+            off_s = hs["off"][:ns + 1].copy()
+            blob_s = hs["blob"][:int(off_s[-1])] if int(off_s[-1]) else np.zeros(0, np.uint8)
+            sig_s = eng.sign_many(hs["sk"][:ns], pk_s, inf_s, blob_s, off_s, hs["nonce"][:ns])
+            v = eng.verify_many(sig_s, pk_s, inf_s, blob_s, off_s)
+            if int(v.max()) != 0:
+                raise SystemExit("small-call verification failed")
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                eng.verify_many(sig_s, pk_s, inf_s, blob_s, off_s)
+                ts.append(time.perf_counter() - t0)
+            small["n%d_ms" % ns] = float(np.mean(ts)) * 1e3
+        small["kernel"] = "k_verify_dist (one signature per six lanes)"
+        out["small_calls"] = small
     return out
 
 
