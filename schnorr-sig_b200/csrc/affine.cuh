@@ -1,15 +1,18 @@
-// Affine-coordinate fast path of the verification (Signature::verify, src/signature.rs:181-205).
+// Fast path of the verification (Signature::verify, src/signature.rs:181-205): point arithmetic in
+// "(X, Y, w)" coordinates -- affine formulas whose field inversions are replaced by a denominator kept in
+// the BASE field.
 //
-// In Fp6 an inversion is cheap relative to a multiplication: through the tower Fp6 = Fp3[u]/(u^2 - v)
-// and the norm Fp3 -> Fp it costs ~45 base-field products plus ONE inversion in the 64-bit field Fp,
-// and the Fp inversions of several independent denominators are shared (Montgomery's trick on the
-// norms).  An affine addition is then 2M + 1S + (share of an inversion) instead of the 11M + 5S of a
-// Jacobian addition, which more than halves the cost of the 150 bucket / table additions of a
-// verification; the doubling chain D_j = 2^j P costs about the same as in Jacobian form.
+// In Fp6 the inverse of d is c / n with the cofactor c in Fp6 and the norm n in Fp (tower Fp6 -> Fp3 -> Fp,
+// ~42 base-field products).  Keeping x = X / w^2, y = Y / w^3 with w in Fp lets every slope denominator be
+// absorbed into w, and scaling by an Fp element costs a sixth of an Fp6 multiplication: an addition is
+// 2M + 1S + cofactor + 7 scalings instead of the 11M + 5S of a Jacobian addition, a doubling 2M + 2S +
+// cofactor + 2 scalings, and no inversion is ever performed.  (A first version used true affine points with
+// Montgomery-shared Fp inversions: one 74-product inversion per chain step made it only 10 % faster than
+// the Jacobian kernel -- profiles/r1_variants.md.)
 //
-// The affine formulas have exceptional inputs (P + P, P + (-P), the identity).  They cannot occur for
+// The affine group law has exceptional inputs (P + P, P + (-P), the identity).  They cannot occur for
 // honest keys except with negligible probability, but adversarial small-order keys reach them, so the
-// fast path DETECTS every such event (a zero denominator, an identity operand it cannot represent)
+// fast path DETECTS every such event (a zero norm, an identity operand it cannot represent)
 // and reports FAST_EXCEPTIONAL; the caller then re-runs that signature through the exact Jacobian
 // routine (curve.cuh: torsion_check_and_mul).  A result that is not flagged is the exact group
 // element, so verdicts stay bit-identical to the reference.
@@ -17,10 +20,6 @@
 #include "curve.cuh"
 
 namespace sb {
-
-struct aff_pt {
-    fp6 x, y;
-};
 
 // adjugate and norm of d in Fp3 with lazily accumulated products (12 products, 4 reductions):
 //   d^-1 = (t0 + t1 v + t2 v^2) / n,   t0 = d0^2 - 7 d1 d2,  t1 = 7 d2^2 - d0 d1,  t2 = d1^2 - d0 d2,
@@ -48,129 +47,6 @@ SB_DEV void fp3_adj_norm_lazy(const fp3& d, fp3& adj, fp_t& norm) {
     wide_mac(w, d1_7, t2);
     norm = wide_reduce(w);
     adj = fp3{{t0, t1, t2}};
-}
-
-// a^-1 for any 64-bit representative a of a non-zero element: 64 squarings + 10 multiplications,
-// the whole chain in non-canonical form.
-//   t31 = a^(2^31 - 1),  t32 = t31^2 a = a^(2^32 - 1),  a^(p-2) = t31^(2^33) t32
-SB_DEV_NOINLINE fp_t fp_inv_chain(fp_t a) {
-    fp_t t2 = fp_mul_nc(fp_sqr_nc(a), a);
-    fp_t t4 = fp_mul_nc(fp_sqr_n_nc(t2, 2), t2);
-    fp_t t8 = fp_mul_nc(fp_sqr_n_nc(t4, 4), t4);
-    fp_t t16 = fp_mul_nc(fp_sqr_n_nc(t8, 8), t8);
-    fp_t t24 = fp_mul_nc(fp_sqr_n_nc(t16, 8), t8);
-    fp_t t28 = fp_mul_nc(fp_sqr_n_nc(t24, 4), t4);
-    fp_t t30 = fp_mul_nc(fp_sqr_n_nc(t28, 2), t2);
-    fp_t t31 = fp_mul_nc(fp_sqr_nc(t30), a);
-    fp_t t32 = fp_mul_nc(fp_sqr_nc(t31), a);
-    return fp_mul_nc(fp_sqr_n_nc(t31, 33), t32);
-}
-
-static constexpr int AFF_MAX_BATCH = 10;
-
-// d[i] <- d[i]^-1 for i < k (k <= AFF_MAX_BATCH) with a single Fp inversion.  Returns the bit mask of the
-// elements that are zero (their slots are left unspecified; the others are still inverted correctly).
-SB_DEV_NOINLINE uint32_t fp6_batch_inv(fp6* d, int k) {
-    fp3 adj[AFF_MAX_BATCH];
-    fp_t nrm[AFF_MAX_BATCH], pre[AFF_MAX_BATCH];
-    uint32_t zero_mask = 0;
-    fp_t run = 1;
-#pragma unroll 1
-    for (int i = 0; i < k; i++) {
-        fp3 a0, a1;
-        fp6_split(d[i], a0, a1);
-        fp3 s0 = fp3_sqr6(a0), s1 = fp3_sqr6(a1);
-        // N = a0^2 - v a1^2,  v (x0, x1, x2) = (7 x2, x0, x1)
-        fp3 nn = fp3{{fp_sub(s0.c[0], fp_mul7(s1.c[2])), fp_sub(s0.c[1], s1.c[0]), fp_sub(s0.c[2], s1.c[1])}};
-        fp_t n;
-        fp3_adj_norm_lazy(nn, adj[i], n);
-        bool z = n == 0;  // the norm of a field element vanishes only for zero
-        if (z) zero_mask |= 1u << i;
-        n = z ? 1 : n;
-        nrm[i] = n;
-        pre[i] = run;
-        run = fp_mul_nc(run, n);
-    }
-    fp_t inv = fp_inv_chain(run);
-#pragma unroll 1
-    for (int i = k - 1; i >= 0; i--) {
-        fp_t ni = fp_mul_nc(inv, pre[i]);  // n_i^-1
-        inv = fp_mul_nc(inv, nrm[i]);
-        fp3 a0, a1;
-        fp6_split(d[i], a0, a1);
-        fp3 s;
-#pragma unroll
-        for (int c = 0; c < 3; c++) s.c[c] = fp_mul_nc(adj[i].c[c], ni);
-        fp3 na1 = fp3{{FP_P - a1.c[0], FP_P - a1.c[1], FP_P - a1.c[2]}};
-        d[i] = fp6_join(fp3_mul(a0, s), fp3_mul(na1, s));
-    }
-    return zero_mask;
-}
-
-// ---- batched affine point operations ---------------------------------------------------------------
-// Per-thread mode of one operation (data-dependent, evaluated with selects: control flow stays uniform)
-enum aff_mode : uint8_t {
-    AOP_NOP = 0,     // leave acc unchanged
-    AOP_ADD = 1,     // acc <- acc + src      (or acc <- 2 acc for a doubling entry)
-    AOP_SUB = 2,     // acc <- acc - src
-    AOP_SET = 3,     // acc <- src            (acc was the identity)
-    AOP_SETNEG = 4,  // acc <- -src
-};
-struct aff_op {
-    aff_pt* acc;
-    const aff_pt* src;  // nullptr (warp-uniform) marks a doubling of acc
-    uint8_t mode;
-};
-SB_DEV uint8_t aff_add_mode(bool acc_empty, bool src_empty, bool neg) {
-    return src_empty ? AOP_NOP : (acc_empty ? (neg ? AOP_SETNEG : AOP_SET) : (neg ? AOP_SUB : AOP_ADD));
-}
-
-// Runs k independent operations with one shared inversion.  All operands are read before anything is
-// written EXCEPT that operation i may read (as src) a point that a LATER operation j > i overwrites
-// (as acc) -- the main loop adds D_j into buckets and then doubles it in the same batch.
-// Returns true when an active operation met a zero denominator (P + P, P - P, doubling a 2-torsion
-// point): the caller must abandon the fast path.
-SB_DEV_NOINLINE bool aff_batch(const aff_op* ops, int k) {
-    fp6 den[AFF_MAX_BATCH];
-#pragma unroll 1
-    for (int i = 0; i < k; i++) {
-        const aff_pt* a = ops[i].acc;
-        const aff_pt* s = ops[i].src;
-        fp6 dd = s ? fp6_sub(a->x, s->x) : fp6_dbl(a->y);
-        bool active = ops[i].mode == AOP_ADD || ops[i].mode == AOP_SUB;
-        den[i] = active ? dd : fp6_one();
-    }
-    bool exceptional = fp6_batch_inv(den, k) != 0;
-#pragma unroll 1
-    for (int i = 0; i < k; i++) {
-        aff_pt* a = ops[i].acc;
-        const aff_pt* s = ops[i].src;
-        uint8_t mode = ops[i].mode;
-        fp6 ax = a->x, ay = a->y, num, bx, sy;
-        if (s) {
-            bx = s->x;
-            sy = s->y;
-            if (mode == AOP_SUB || mode == AOP_SETNEG) sy = fp6_neg(sy);
-            num = fp6_sub(ay, sy);
-        } else {
-            bx = ax;
-            sy = ay;
-            fp6 xx = fp6_sqr(ax);
-            num = fp6_add(fp6_dbl(xx), xx);
-            num.c[0] = fp_add(num.c[0], 1);  // 3 x^2 + a, a = 1
-        }
-        fp6 lam = fp6_mul(num, den[i]);
-        fp6 x3 = fp6_sub(fp6_sub(fp6_sqr(lam), ax), bx);
-        fp6 y3 = fp6_sub(fp6_mul(lam, fp6_sub(ax, x3)), ay);
-        bool active = mode == AOP_ADD || mode == AOP_SUB;
-        bool set = mode == AOP_SET || mode == AOP_SETNEG;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-            a->x.c[c] = active ? x3.c[c] : (set ? bx.c[c] : ax.c[c]);
-            a->y.c[c] = active ? y3.c[c] : (set ? sy.c[c] : ay.c[c]);
-        }
-    }
-    return exceptional;
 }
 
 // ---- Jacobian coordinates with the denominator in the BASE field -------------------------------------

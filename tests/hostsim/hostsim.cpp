@@ -171,21 +171,9 @@ API int hs_verify_one(const uint8_t* sig81, const uint8_t* pk96, int pk_inf, con
     return verify_points(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &d);
 }
 
-// ---- affine fast path (affine.cuh) ----
-API int hs_fp6_batch_inv(uint64_t* d, int k) { return (int)fp6_batch_inv(reinterpret_cast<fp6*>(d), k); }
-API uint64_t hs_fp_inv_chain(uint64_t a) { return fp_canon(fp_inv_chain(a)); }
-// one batched affine operation list: acc[i] (96 B each, in/out), src[i] (96 B each), mode[i]; is_dbl[i] marks doublings
-API int hs_aff_batch(uint8_t* acc96, const uint8_t* src96, const uint8_t* mode, const uint8_t* is_dbl, int k) {
-    aff_op ops[AFF_MAX_BATCH];
-    for (int i = 0; i < k; i++) {
-        ops[i].acc = reinterpret_cast<aff_pt*>(acc96 + 96 * i);
-        ops[i].src = is_dbl[i] ? nullptr : reinterpret_cast<const aff_pt*>(src96 + 96 * i);
-        ops[i].mode = mode[i];
-    }
-    return aff_batch(ops, k);
-}
+// ---- fast path in (X, Y, w) coordinates (affine.cuh) ----
 // returns fast_result; out96 = h*P + e*G when FAST_TORSION_FREE / FAST_NOT_TORSION_FREE
-API int hs_verify_core_affine(const uint8_t* p96, const uint8_t* h32, const uint8_t* e32, uint8_t* out96) {
+API int hs_verify_core_fast(const uint8_t* p96, const uint8_t* h32, const uint8_t* e32, uint8_t* out96) {
     build_gtab();
     fp6 x, y;
     memcpy(x.c, p96, 48);

@@ -258,65 +258,10 @@ def test_shared_doubling_core(hostsim):
     assert hostsim.hs_torsion_check_and_mul(p(KAT96), 1, p(H), p(out), C.byref(oi)) == 1 and oi.value == 1
 
 
-# ---- affine fast path (schnorr-sig_b200/csrc/affine.cuh) --------------------------------------------
+# ---- fast path in (X, Y, w) coordinates (schnorr-sig_b200/csrc/affine.cuh) ------------------------
 
-def test_batch_inversion(hostsim):
-    hostsim.hs_fp_inv_chain.restype = C.c_uint64
-    rng = np.random.default_rng(31)
-    for a in [1, 2, 7, o.P - 1, 2**32, 2**32 - 1] + [int(x) for x in rand_fp(rng, 40) if x]:
-        assert hostsim.hs_fp_inv_chain(C.c_uint64(a)) == pow(a, o.P - 2, o.P)
-    assert hostsim.hs_fp_inv_chain(C.c_uint64(o.P + 5)) == pow(5, o.P - 2, o.P)     # non-canonical representative
-    special = [np.array([1, 0, 0, 0, 0, 0], dtype=np.uint64), np.array([0, 0, 0, 0, 0, 1], dtype=np.uint64),
-               np.array([0, 3, 0, 0, 0, 0], dtype=np.uint64), np.array([o.P - 1] * 6, dtype=np.uint64),
-               np.array([5, 0, 9, 0, 11, 0], dtype=np.uint64)]
-    for k in (1, 2, 3, 4, 7, 10):
-        elems = [rand_fp6(rng) for _ in range(k)]
-        elems[0] = special[k % len(special)]
-        d = np.concatenate(elems).astype(np.uint64)
-        assert hostsim.hs_fp6_batch_inv(p(d), k) == 0
-        for i in range(k):
-            assert tuple(int(x) for x in d[6 * i:6 * i + 6]) == o.f6_inv(tuple(int(x) for x in elems[i]))
-    # zero elements are reported and do not disturb the others
-    elems = [rand_fp6(rng) for _ in range(5)]
-    elems[1] = np.zeros(6, dtype=np.uint64)
-    elems[4] = np.zeros(6, dtype=np.uint64)
-    d = np.concatenate(elems).astype(np.uint64)
-    assert hostsim.hs_fp6_batch_inv(p(d), 5) == 0b10010
-    for i in (0, 2, 3):
-        assert tuple(int(x) for x in d[6 * i:6 * i + 6]) == o.f6_inv(tuple(int(x) for x in elems[i]))
-
-
-def test_affine_batch_operations(hostsim):
-    rng = np.random.default_rng(32)
-    G = o.generator()
-    kat = (o.KAT_X, o.KAT_Y)
-    pts = [o.pt_mul(G, int_le(s)) for s in rand_scalars(rng, 9)] + [kat]
-    NOP, ADD, SUB, SET, SETNEG = 0, 1, 2, 3, 4
-    acc = np.concatenate([pt_to96(a) for a in pts]).copy()
-    src = np.concatenate([pt_to96(pts[(i + 3) % 10]) for i in range(10)]).copy()
-    mode = np.array([ADD, SUB, SET, SETNEG, NOP, ADD, ADD, SUB, ADD, ADD], dtype=np.uint8)
-    dbl = np.array([0, 0, 0, 0, 0, 1, 0, 0, 1, 0], dtype=np.uint8)
-    assert hostsim.hs_aff_batch(p(acc), p(src), p(mode), p(dbl), 10) == 0
-    for i in range(10):
-        a, s = pts[i], pts[(i + 3) % 10]
-        want = {NOP: a, ADD: o.pt_add(a, a) if dbl[i] else o.pt_add(a, s), SUB: o.pt_add(a, o.pt_neg(s)), SET: s,
-                SETNEG: o.pt_neg(s)}[int(mode[i])]
-        assert pt_from96(acc[96 * i:96 * i + 96]) == want
-    # exceptional inputs are reported: P + P, P - P, doubling a point of order 2; inactive slots never are
-    a96 = pt_to96(pts[0])
-    for m, s, d, want in ((ADD, pts[0], 0, 1), (SUB, pts[0], 0, 1), (ADD, o.pt_neg(pts[0]), 0, 1), (NOP, pts[0], 0, 0),
-                          (SET, pts[0], 0, 0)):
-        acc = np.concatenate([a96, pt_to96(pts[1])]).copy()
-        src = np.concatenate([pt_to96(s), pt_to96(pts[2])]).copy()
-        assert hostsim.hs_aff_batch(p(acc), p(src), p(np.array([m, ADD], dtype=np.uint8)), p(np.array([d, 0], dtype=np.uint8)), 2) == want
-        assert pt_from96(acc[96:]) == o.pt_add(pts[1], pts[2])          # the healthy slot is still exact
-    t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
-    acc = pt_to96(t2).copy()
-    assert hostsim.hs_aff_batch(p(acc), p(acc.copy()), p(np.array([ADD], dtype=np.uint8)), p(np.array([1], dtype=np.uint8)), 1) == 1
-
-
-def test_verify_core_affine(hostsim):
-    """[q]P == O and h*P + e*G from the affine chain; exceptional keys are reported, never mis-evaluated."""
+def test_verify_core_fast(hostsim):
+    """[q]P == O and h*P + e*G from the (X, Y, w) chain; exceptional keys are reported, never mis-evaluated."""
     rng = np.random.default_rng(33)
     G = o.generator()
     kat = (o.KAT_X, o.KAT_Y)
@@ -327,7 +272,7 @@ def test_verify_core_affine(hostsim):
     def run(pt, h, e):
         H = np.frombuffer(h.to_bytes(32, "little"), dtype=np.uint8).copy()
         E = np.frombuffer(e.to_bytes(32, "little"), dtype=np.uint8).copy()
-        return hostsim.hs_verify_core_affine(p(pt_to96(pt)), p(H), p(E), p(out))
+        return hostsim.hs_verify_core_fast(p(pt_to96(pt)), p(H), p(E), p(out))
 
     good = [o.pt_mul(G, 12345), o.pt_mul(G, int_le(rand_scalars(rng, 1)[0]))]
     hs = [0, 1, 2, 8, 0x8888888888888888, o.Q - 1, 2**255 - 1] + [int_le(s) for s in rand_scalars(rng, 3)]

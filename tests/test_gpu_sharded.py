@@ -130,3 +130,29 @@ def test_mid_size_random_faults_against_oracle():
     ok = f["sigs"][:, :48].view(np.uint64).max(axis=1) < np.uint64(0xFFFFFFFF00000001)
     cd = cref.hash_messages(f["sigs"][:, :48].copy(), f["pk"], f["blob"], f["off"], cref.default_threads())
     assert np.array_equal(d[ok], cd[ok])
+
+
+def test_three_verification_kernels_agree_at_2_17():
+    """k_verify_fast (one signature per thread), k_verify_dist (six lanes per signature) and the exact Jacobian
+    k_verify return the same verdict vector on 2^17 device-signed signatures with ragged messages and 1/64 faults."""
+    import schnorr_sig_b200 as s
+    eng = s.default_engine(0)
+    n = 1 << 17
+    w = s.synth.signed_workload(eng, 0xC0FFEE, n, msg_len=8)
+    f = s.synth.inject_faults(w, every=64)
+    got = {}
+    try:
+        eng.set_dist_threshold(0)
+        got["fast"] = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        assert eng.last_exact_count() == 0
+        eng.set_dist_threshold(2**62)
+        got["dist"] = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        assert eng.last_exact_count() == 0
+        eng.set_exact_only(True)
+        got["exact"] = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+    finally:
+        eng.set_exact_only(False)
+        eng.set_dist_threshold(10240)
+    assert np.array_equal(got["fast"], f["expect"])
+    assert np.array_equal(got["dist"], f["expect"])
+    assert np.array_equal(got["exact"], f["expect"])
