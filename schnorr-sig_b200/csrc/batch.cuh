@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
                                                        int* __restrict__ bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = in.n;
-    if (i >= n) return;
+    bool live = i < n;
+    uint64_t off = live ? msg_off[i] : 0, len = live ? msg_off[i + 1] - off : 0;
+    bool hash_sync = block_uniform_permutations(live ? hash_message_permutations(len) : -1);
+    if (!live) return;
     uint8_t fl = in.flags[i];
     fp6 sx = load_fp6_planes(in.planes, 0, n, i);
     scalar e = load_scalar_planes(in.planes, 3, n, i);
@@ -66,16 +69,15 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
     scalar s = sc_from_u256(sc_load_le(rand32 + 32 * i));
     scalar s_r = sc_zero(), s_p = sc_zero(), l = sc_zero();
     fp6 rx = fp6_zero(), ry = fp6_zero();
+    bool r_inf = true;
+    if (ok) ok = decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);  // unwrap panic, src/batch.rs:104
+    // every live thread hashes (a malformed item's digest is simply unused): the permutation barriers stay matched,
+    // and the barrier at its start re-aligns the warps after the divergent square-root loops
+    scalar h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
     if (ok) {
-        bool r_inf;
-        ok = decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);  // unwrap panic, src/batch.rs:104
-        if (ok) {
-            uint64_t off = msg_off[i];
-            scalar h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
-            l = sc_mul(s, e);                     // src/batch.rs:92-97
-            s_r = r_inf ? sc_zero() : s;          // identity contributes nothing
-            s_p = pk_inf ? sc_zero() : sc_mul(h, s);  // src/batch.rs:109-111
-        }
+        l = sc_mul(s, e);                     // src/batch.rs:92-97
+        s_r = r_inf ? sc_zero() : s;          // identity contributes nothing
+        s_p = pk_inf ? sc_zero() : sc_mul(h, s);  // src/batch.rs:109-111
     }
     if (!ok) atomicOr(bad, 1);
     fp6 npy = fp6_neg(py);  // src/batch.rs:106

@@ -101,7 +101,40 @@ SB_DEV fp_t rescue_inv_sbox(fp_t x) {
     return fp_canon(x);
 }
 
-SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
+// Code-size discipline (ncu: the fully unrolled permutation was 4.9 k instructions and ran at a 76 % instruction-cache
+// hit rate, "no instruction" being the top stall of k_hash and k_batch_prepare): ONE copy of the MDS layer, of the
+// forward S-box group and of the inverse S-box group, driven by rolled loops over the two half-rounds and the two
+// groups of six state elements.
+#ifndef SB_RESCUE_COMPACT
+#define SB_RESCUE_COMPACT 1
+#endif
+// `sync`: block barrier per half-round.  Warps that run the permutation in step share instruction-cache lines (same
+// effect as SB_PHASE_SYNC in the point loops); only legal when EVERY live thread of the block runs the same number of
+// permutations -- the kernels vote on that (block_uniform_permutations) and pass false otherwise.
+#if defined(__CUDA_ARCH__)
+#define SB_HASH_SYNC(flag) do { if (flag) __syncthreads(); } while (0)
+#else
+#define SB_HASH_SYNC(flag) do { (void)(flag); } while (0)
+#endif
+SB_DEV_NOINLINE void rescue_permutation(fp_t* s, bool sync = false) {
+#if SB_RESCUE_COMPACT
+#pragma unroll 1
+    for (int hr = 0; hr < 2 * RESCUE_ROUNDS; hr++) {
+        SB_HASH_SYNC(sync);
+        if ((hr & 1) == 0) {
+#pragma unroll 1
+            for (int g = 0; g < 12; g += 6) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) s[g + i] = rescue_sbox(s[g + i]);
+            }
+        } else {
+            // inverse S-box: 6 independent chains at a time (ILP), one rolled copy of the code for both halves
+#pragma unroll 1
+            for (int g = 0; g < 12; g += 6) rescue_inv_sbox_lanes<6>(s + g);
+        }
+        rescue_mds_ark(s, hr);
+    }
+#else
 #pragma unroll 1
     for (int r = 0; r < RESCUE_ROUNDS; r++) {
 #pragma unroll
@@ -112,6 +145,7 @@ SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
         for (int g = 0; g < 12; g += 6) rescue_inv_sbox_lanes<6>(s + g);
         rescue_mds_ark(s, 2 * r + 1);
     }
+#endif
 }
 
 // Streaming sponge = RescueHash::hash_field: additive absorption into state[0..8], permutation per
@@ -119,19 +153,23 @@ SB_DEV_NOINLINE void rescue_permutation(fp_t* s) {
 struct rescue_sponge {
     fp_t s[12];
     int i;
+    bool sync;
 };
-SB_DEV void sponge_init(rescue_sponge& sp) {
+SB_DEV void sponge_init(rescue_sponge& sp, bool sync = false) {
 #pragma unroll
     for (int k = 0; k < 12; k++) sp.s[k] = 0;
     sp.i = 0;
+    sp.sync = sync;
 }
+// number of permutations hash_message runs for a message of `len` bytes (13 fixed elements + ceil(len / 7), rate 8)
+SB_DEV int hash_message_permutations(uint64_t len) { return (int)((13 + (len + 6) / 7 + 7) / 8); }
 SB_DEV void sponge_absorb(rescue_sponge& sp, fp_t e) {
     // dynamic index into a register array would spill: select statically
 #pragma unroll
     for (int k = 0; k < 8; k++)
         if (k == sp.i) sp.s[k] = fp_add(sp.s[k], e);
     if (++sp.i == 8) {
-        rescue_permutation(sp.s);
+        rescue_permutation(sp.s, sp.sync);
         sp.i = 0;
     }
 }
@@ -140,7 +178,7 @@ SB_DEV void sponge_finish(rescue_sponge& sp) {
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (k == sp.i) sp.s[k] = fp_add(sp.s[k], 1);
-        rescue_permutation(sp.s);
+        rescue_permutation(sp.s, sp.sync);
     }
 }
 
@@ -154,13 +192,14 @@ SB_DEV uint64_t load_le_bytes(const uint8_t* p, int n) {
 // hash_message (src/signature.rs:274-306): absorb R.x (6), P.x (6), P.y[0] (1), then the message in
 // 7-byte little-endian chunks; a short tail chunk gets a 0x01 marker byte after its last byte.
 // Returns the digest as 4 field elements (Digest::to_bytes = their little-endian bytes).
-SB_DEV void hash_message(const fp6& rx, const fp6& px, fp_t py0, const uint8_t* msg, uint64_t len, fp_t* digest) {
+SB_DEV void hash_message(const fp6& rx, const fp6& px, fp_t py0, const uint8_t* msg, uint64_t len, fp_t* digest,
+                         bool sync = false) {
     rescue_sponge sp;
-    sponge_init(sp);
+    sponge_init(sp, sync);
     // first block is always full: 8 of the 13 fixed elements
     sp.s[0] = rx.c[0]; sp.s[1] = rx.c[1]; sp.s[2] = rx.c[2]; sp.s[3] = rx.c[3];
     sp.s[4] = rx.c[4]; sp.s[5] = rx.c[5]; sp.s[6] = px.c[0]; sp.s[7] = px.c[1];
-    rescue_permutation(sp.s);
+    rescue_permutation(sp.s, sync);
     sp.s[0] = fp_add(sp.s[0], px.c[2]); sp.s[1] = fp_add(sp.s[1], px.c[3]);
     sp.s[2] = fp_add(sp.s[2], px.c[4]); sp.s[3] = fp_add(sp.s[3], px.c[5]);
     sp.s[4] = fp_add(sp.s[4], py0);

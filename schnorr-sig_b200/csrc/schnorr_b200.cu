@@ -112,6 +112,24 @@ __device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
     return v;
 }
 
+// True when every thread of the block that is going to hash (np >= 0) runs the same number of Rescue permutations:
+// the permutation then takes a block barrier per half-round (rescue.cuh), which keeps the warps of the block on the
+// same instruction-cache lines.  Must be called by ALL threads of the block, before any early return.
+__device__ __forceinline__ bool block_uniform_permutations(int np) {
+    __shared__ int s_np_min, s_np_max;
+    if (threadIdx.x == 0) {
+        s_np_min = 1 << 30;
+        s_np_max = -1;
+    }
+    __syncthreads();
+    if (np >= 0) {
+        atomicMin(&s_np_min, np);
+        atomicMax(&s_np_max, np);
+    }
+    __syncthreads();
+    return s_np_min >= s_np_max;
+}
+
 // AoS -> SoA.  The 81-byte signature records of a block are staged through shared memory with
 // coalesced 16-byte loads; public keys (96 B, 8-byte aligned) are read directly.
 static constexpr int INGEST_THREADS = 128;
@@ -229,8 +247,12 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
     };
     __shared__ d_slot s_d[VERIFY_THREADS];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= in.n) return;
-    uint8_t fl = in.flags[i];
+    bool live = i < in.n;
+    uint8_t fl = live ? in.flags[i] : FL_MALFORMED;
+    bool hashes = live && !(fl & (FL_MALFORMED | FL_PK_INF));
+    uint64_t off = hashes ? msg_off[i] : 0, len = hashes ? msg_off[i + 1] - off : 0;
+    bool hash_sync = block_uniform_permutations(hashes ? hash_message_permutations(len) : -1);
+    if (!live) return;
     if (fl & FL_MALFORMED) {
         verdicts[i] = VERDICT_MALFORMED;
         return;
@@ -241,9 +263,11 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
     fp6 py = load_fp6_planes(in.planes, 8, in.n, i);
     bool pk_inf = fl & FL_PK_INF;
     bool x_ok = !(fl & FL_X_BAD);
-    uint64_t off = msg_off[i];
     scalar h = sc_zero();
-    if (x_ok && !pk_inf) h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+    if (!pk_inf) {  // an item with a malformed x hashes too (result unused): every hashing thread takes the same barriers
+        h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
+        if (!x_ok) h = sc_zero();
+    }
     uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
     verdicts[i] = v;
     if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
@@ -312,7 +336,10 @@ __global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* 
                                                        const uint64_t* __restrict__ msg_off,
                                                        uint8_t* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    bool live = i < n;
+    uint64_t off = live ? msg_off[i] : 0, len = live ? msg_off[i + 1] - off : 0;
+    bool hash_sync = block_uniform_permutations(live ? hash_message_permutations(len) : -1);
+    if (!live) return;
     const uint64_t* r = reinterpret_cast<const uint64_t*>(rx48 + i * 48);
     const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
     fp6 rx, px;
@@ -323,8 +350,7 @@ __global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* 
     }
     fp_t py0 = p[6];
     fp_t d[4];
-    uint64_t off = msg_off[i];
-    hash_message(rx, px, py0, msgs + off, msg_off[i + 1] - off, d);
+    hash_message(rx, px, py0, msgs + off, len, d, hash_sync);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + i * 32);
     o[0] = make_ulonglong2(d[0], d[1]);
     o[1] = make_ulonglong2(d[2], d[3]);

@@ -49,11 +49,11 @@ SB_DEV uint8_t verify_points_fast(const fp6& sig_x, bool x_ok, const scalar& e, 
 // Challenge: h = Scalar::from_bits_vartime(hash_message(R.x, P, m))  (src/signature.rs:188-192).
 // The identity public key hashes as x = y = 0 (its in-memory coordinates).
 SB_DEV scalar challenge_scalar(const fp6& sig_x, const fp6& pk_x, const fp6& pk_y, bool pk_inf, const uint8_t* msg,
-                               uint64_t len) {
+                               uint64_t len, bool sync = false) {
     fp6 px = pk_inf ? fp6_zero() : pk_x;
     fp_t py0 = pk_inf ? 0 : pk_y.c[0];
     fp_t d[4];
-    hash_message(sig_x, px, py0, msg, len, d);
+    hash_message(sig_x, px, py0, msg, len, d, sync);
     return digest_to_scalar(d);
 }
 
