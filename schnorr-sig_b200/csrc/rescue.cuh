@@ -105,6 +105,10 @@ SB_DEV fp_t rescue_inv_sbox(fp_t x) {
 // hit rate, "no instruction" being the top stall of k_hash and k_batch_prepare): ONE copy of the MDS layer, of the
 // forward S-box group and of the inverse S-box group, driven by rolled loops over the two half-rounds and the two
 // groups of six state elements.
+// state elements per S-box group (independent chains interleaved for ILP; smaller = less code)
+#ifndef SB_SBOX_LANES
+#define SB_SBOX_LANES 6
+#endif
 #ifndef SB_RESCUE_COMPACT
 #define SB_RESCUE_COMPACT 1
 #endif
@@ -123,14 +127,14 @@ SB_DEV_NOINLINE void rescue_permutation(fp_t* s, bool sync = false) {
         SB_HASH_SYNC(sync);
         if ((hr & 1) == 0) {
 #pragma unroll 1
-            for (int g = 0; g < 12; g += 6) {
+            for (int g = 0; g < 12; g += SB_SBOX_LANES) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) s[g + i] = rescue_sbox(s[g + i]);
+                for (int i = 0; i < SB_SBOX_LANES; i++) s[g + i] = rescue_sbox(s[g + i]);
             }
         } else {
             // inverse S-box: 6 independent chains at a time (ILP), one rolled copy of the code for both halves
 #pragma unroll 1
-            for (int g = 0; g < 12; g += 6) rescue_inv_sbox_lanes<6>(s + g);
+            for (int g = 0; g < 12; g += SB_SBOX_LANES) rescue_inv_sbox_lanes<SB_SBOX_LANES>(s + g);
         }
         rescue_mds_ark(s, hr);
     }
