@@ -226,6 +226,11 @@ SB_DEV void jf_dbl_exact(jf_pt* acc) {
     if (jf_dbl(acc)) acc->w = 0;
 }
 
+// block barrier every (mask + 1) steps of the doubling chain
+#ifndef SB_CHAIN_SYNC_MASK
+#define SB_CHAIN_SYNC_MASK 3
+#endif
+
 enum fast_result : int {
     FAST_TORSION_FREE = 0,      // [q]P == O, h*P + e*G computed
     FAST_NOT_TORSION_FREE = 1,  // [q]P != O
@@ -252,7 +257,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     Dp->w = 1;
 #pragma unroll 1
     for (int j = 0; j < 256; j++) {
-        if ((j & 3) == 0) SB_PHASE_SYNC(1);
+        if ((j & SB_CHAIN_SYNC_MASK) == 0) SB_PHASE_SYNC(1);
         int dq = SB_QWNAF(j);
         if (dq != 0) {  // warp-uniform
             int idx = (dq < 0 ? -dq : dq) >> 1;
