@@ -177,10 +177,10 @@ __device__ __noinline__ void drescue_permutation(unsigned mask, fp_t* lo_hi, int
     lo_hi[0] = s[0];
     lo_hi[1] = s[1];
 }
-// hash_message + digest -> challenge scalar (rescue.cuh: hash_message, verify.cuh: challenge_scalar); rx, px, py =
-// the lane's coefficients; msg/len are the group's message
-__device__ scalar dchallenge_scalar(unsigned mask, fp_t rx, fp_t px, fp_t py, const uint8_t* msg, uint64_t len, int k,
-                                    int gbase, const uint32_t* mds2) {
+// hash_message (rescue.cuh) on six lanes; rx, px, py = the lane's coefficients (py: only lane 0's P.y[0] is used);
+// msg/len are the group's message; the digest (4 elements) is returned on every lane
+__device__ void dhash_message(unsigned mask, fp_t rx, fp_t px, fp_t py, const uint8_t* msg, uint64_t len, int k, int gbase,
+                              const uint32_t* mds2, fp_t* d) {
     fp_t s[2];
     s[0] = rx;               // s[0..5] = R.x
     s[1] = k < 2 ? px : 0;   // s[6], s[7] = P.x[0..1]; capacity = 0
@@ -208,9 +208,14 @@ __device__ scalar dchallenge_scalar(unsigned mask, fp_t rx, fp_t px, fp_t py, co
         else s[0] = fp_add(s[0], v);
         drescue_permutation(mask, s, k, gbase, mds2);
     }
-    fp_t d[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = dshfl(mask, s[0], gbase + i);
+}
+// challenge scalar (verify.cuh: challenge_scalar)
+__device__ scalar dchallenge_scalar(unsigned mask, fp_t rx, fp_t px, fp_t py, const uint8_t* msg, uint64_t len, int k,
+                                    int gbase, const uint32_t* mds2) {
+    fp_t d[4];
+    dhash_message(mask, rx, px, py, msg, len, k, gbase, mds2, d);
     return digest_to_scalar(d);
 }
 

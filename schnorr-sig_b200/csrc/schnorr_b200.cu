@@ -356,6 +356,30 @@ __global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* 
     o[1] = make_ulonglong2(d[2], d[3]);
 }
 
+// K1 for small calls: one message per group of six lanes (dist.cuh), five messages per warp
+__global__ void __launch_bounds__(DIST_THREADS) k_hash_dist(size_t n, const uint8_t* __restrict__ rx48,
+                                                            const uint8_t* __restrict__ pk96,
+                                                            const uint8_t* __restrict__ msgs,
+                                                            const uint64_t* __restrict__ msg_off,
+                                                            uint8_t* __restrict__ digests) {
+    __shared__ uint32_t s_mds2[24];
+    if (threadIdx.x < 24) s_mds2[threadIdx.x] = c_mds_row[threadIdx.x % 12];
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g = lane / 6, k = lane % 6;
+    if (g >= 5) return;
+    size_t i = ((size_t)blockIdx.x * (DIST_THREADS / 32) + warp) * 5 + g;
+    if (i >= n) return;
+    int gbase = 6 * g;
+    unsigned mask = 0x3fu << gbase;
+    const uint64_t* r = reinterpret_cast<const uint64_t*>(rx48 + i * 48);
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    uint64_t off = msg_off[i];
+    fp_t d[4];
+    dhash_message(mask, r[k], p[k], p[6 + k], msgs + off, msg_off[i + 1] - off, k, gbase, s_mds2, d);
+    if (k < 4) reinterpret_cast<uint64_t*>(digests + i * 32)[k] = d[k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: fixed-base multiplication -> key generation and the device signer
 // ------------------------------------------------------------------------------------------------
@@ -753,7 +777,10 @@ int schnorr_b200_hash_messages_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    k_hash<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, ctx->stream>>>(n, rx48, pk96, msgs, msg_off, digests);
+    if (n <= ctx->dist_max)
+        k_hash_dist<<<grid_for(n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, ctx->stream>>>(n, rx48, pk96, msgs, msg_off, digests);
+    else
+        k_hash<<<grid_for(n, HASH_THREADS), HASH_THREADS, 0, ctx->stream>>>(n, rx48, pk96, msgs, msg_off, digests);
     cudaEventRecord(ctx->ev_k1, ctx->stream);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -35,9 +35,13 @@ def test_hash_messages_bit_exact(eng, n, lens):
     blob, off = pack_msgs(msgs)
     rx = rand_fp(rng, n * 6).view(np.uint8).reshape(n, 48)
     pk = rand_fp(rng, n * 12).view(np.uint8).reshape(n, 96)
-    got = eng.hash_messages(rx, pk, blob, off)
     want = cref.hash_messages(rx, pk, blob, off, cref.default_threads())
-    assert np.array_equal(got, want)
+    assert np.array_equal(eng.hash_messages(rx, pk, blob, off), want)       # k_hash_dist (small calls)
+    eng.set_dist_threshold(0)
+    try:
+        assert np.array_equal(eng.hash_messages(rx, pk, blob, off), want)   # k_hash (one message per thread)
+    finally:
+        eng.set_dist_threshold(10240)
 
 
 def test_hash_padding_collision_preserved(eng):
