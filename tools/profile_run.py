@@ -61,7 +61,7 @@ def main():
         for p in a.paths.split(","):
             if p == "verify":
                 timed("verify", lambda: eng.verify_many_dev(n, d_sigs, d_pk, d_inf, d_blob, d_off, d_out))
-                assert int(d_out.max().item()) == 0
+                assert int(d_out.max().item()) == 0 or os.environ.get("SB_PROFILE_NO_CHECK")
                 print("  handed to the exact kernel: %d of %d" % (eng.last_exact_count(), n), flush=True)
             elif p == "verify_dist":
                 eng.set_dist_threshold(2**62)
