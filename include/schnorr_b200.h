@@ -60,8 +60,8 @@ uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx *ctx);
 /* Device time (CUDA events on the context stream) of the dominant kernel of the last *_dev call:
  * k_verify (verify_many), k_hash (hash_messages), k_msm_segment_sum (batch).  Synchronises on it. */
 int schnorr_b200_last_kernel_ms(schnorr_b200_ctx *ctx, float *ms);
-/* Single verification runs an affine-coordinate fast path and re-runs the items that hit an exceptional case of
- * the affine group law (identity / small-order keys, colliding partial sums) through the exact Jacobian kernel.
+/* Single verification runs a fast path (inversion-free affine formulas, denominators kept in Fp) and re-runs the items
+ * that hit one of its exceptional cases (identity / small-order keys, colliding partial sums) through the exact Jacobian kernel.
  * exact_only = 1 sends everything through the exact kernel (A/B measurements, tests; also env SB_VERIFY_EXACT=1).
  * last_exact_count: how many items of the last verify_many* call took the exact kernel (synchronises). */
 int schnorr_b200_set_exact_only(schnorr_b200_ctx *ctx, int exact_only);

@@ -43,7 +43,7 @@ struct schnorr_b200_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
-    bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the affine fast path (A/B measurements, tests)
+    bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the fast path (A/B measurements, tests)
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
     };
     __shared__ d_slot s_d[VERIFY_THREADS];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (work_list) {  // exact pass over the items the affine fast path handed back
+    if (work_list) {  // exact pass over the items the fast path handed back
         if (i >= *work_count) return;
         i = work_list[i];
     }
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
     verdicts[i] = verify_points(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
 }
 
-// K2 fast path: the same verdicts through affine point arithmetic with shared inversions (affine.cuh).
-// Items that meet an exceptional case of the affine group law (identity / small-order keys, colliding
+// K2 fast path: the same verdicts through point arithmetic in (X, Y, w) coordinates, w in Fp (affine.cuh).
+// Items that meet an exceptional case of the chord-and-tangent formulas (identity / small-order keys, colliding
 // partial sums: ~0.1 % of honest inputs) are appended to `work_list` and finished by k_verify.
 #ifndef VERIFY_FAST_MIN_BLOCKS
 #define VERIFY_FAST_MIN_BLOCKS 2
@@ -616,7 +616,7 @@ static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t by
 
 #include "batch.cuh"
 
-// Signature::verify over an ingested SoA batch: affine fast path, then the exact kernel over the handful of
+// Signature::verify over an ingested SoA batch: fast path (per-thread or warp-cooperative by call size), then the exact kernel over the handful of
 // items it handed back.  `list_base` = first element of this batch in the per-call work list (pipelined chunks
 // use disjoint regions), `counter` = index of its counter.
 static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint8_t* msgs, const uint64_t* msg_off,

@@ -15,7 +15,7 @@ enum verdict_t : uint8_t {
     VERDICT_INVALID_PUBLIC_KEY = 1,  // SignatureError::InvalidPublicKey  src/error.rs:15
     VERDICT_INVALID_SIGNATURE = 2,   // SignatureError::InvalidSignature  src/error.rs:17
     VERDICT_MALFORMED = 3,           // inputs on which the reference panics / that its types cannot hold
-    VERDICT_NEEDS_EXACT = 0xff,      // internal: the affine fast path met an exceptional case (never returned to callers)
+    VERDICT_NEEDS_EXACT = 0xff,      // internal: the fast path met an exceptional case (never returned to callers)
 };
 
 // Everything after the challenge hash: subgroup check, h*P + e*G, x-only comparison.
@@ -32,8 +32,8 @@ SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const
     return jac_x_equals(r, sig_x) ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
 }
 
-// Same verdicts through the affine fast path (affine.cuh).  VERDICT_NEEDS_EXACT asks the caller to run
-// verify_points on this item: identity key, or an exceptional case of the affine group law.
+// Same verdicts through the fast path in (X, Y, w) coordinates (affine.cuh).  VERDICT_NEEDS_EXACT asks the caller to run
+// verify_points on this item: identity key, or an exceptional case of the chord-and-tangent formulas.
 SB_DEV uint8_t verify_points_fast(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
                                   const scalar& h, const uint64_t* __restrict__ gtab, jf_pt* d_storage) {
     if (pk_inf) return VERDICT_NEEDS_EXACT;

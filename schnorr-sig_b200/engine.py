@@ -93,7 +93,7 @@ class Engine:
         self._check(self._L.schnorr_b200_set_dist_threshold(self._h, int(max_signatures)), "set_dist_threshold")
 
     def last_exact_count(self) -> int:
-        """Items of the last verify_many* call that the affine fast path handed to the exact kernel."""
+        """Items of the last verify_many* call that the fast path handed to the exact kernel."""
         c = C.c_uint64(0)
         self._check(self._L.schnorr_b200_last_exact_count(self._h, C.byref(c)), "last_exact_count")
         return int(c.value)
