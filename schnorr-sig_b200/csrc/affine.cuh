@@ -127,6 +127,9 @@ SB_SCALE_FN fp6 fp6_scale_diff(fp6 a, fp_t s, fp6 b, fp_t t) {
 }
 
 // p <- 2 p.  Returns true on the exceptional input (a point of order 2: the result would be the identity).
+// FUSED: Y3 through fp6_mul_sub_scaled (1 % faster in k_verify_fast, but its 38 argument registers cost
+// k_msm_segment_sum a resident block -> the MSM kernels use the plain form)
+template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     fp6 X = p->X, Y = p->Y, c;
     fp_t w = p->w, n;
@@ -140,7 +143,9 @@ SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
     fp6 A = fp6_scale(X, m2);
     fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
-    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
+    fp6 Y3;
+    if (FUSED) Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
+    else Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
     p->X = X3;
     p->Y = Y3;
     p->w = fp_mul(m, w);
@@ -161,6 +166,7 @@ SB_DEV uint8_t jf_add_mode(bool acc_empty, bool src_empty, bool neg) {
 
 // acc <- acc (+|-) src according to `mode`.  Returns true when an ACTIVE addition met x(acc) == x(src)
 // (P + P or P - P): the fast path cannot represent / evaluate those and must be abandoned.
+template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
     fp6 X1 = acc->X, Y1 = acc->Y, X2 = src->X, Y2 = src->Y;
     fp_t w1 = acc->w, w2 = src->w;
@@ -176,7 +182,9 @@ SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
     fp6 A = fp6_scale(X1, fp_mul_nc(n2, w2s));   // n^2 U1 = x1 w3^2
     fp6 B = fp6_scale(X2, fp_mul_nc(n2, w1s));   // n^2 U2 = x2 w3^2
     fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), B);
-    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));   // ... - y1 w3^3
+    fp6 Y3;                                      // L (x1 w3^2 - X3) - y1 w3^3
+    if (FUSED) Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y1, fp_mul_nc(n3, w2c));
+    else Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));
     fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
     bool wanted = mode == JOP_ADD || mode == JOP_SUB;
     bool active = wanted && n != 0;  // on the exceptional input acc is left untouched
@@ -228,7 +236,7 @@ SB_DEV void jf_dbl_exact(jf_pt* acc) {
 
 // block barrier every (mask + 1) steps of the doubling chain
 #ifndef SB_CHAIN_SYNC_MASK
-#define SB_CHAIN_SYNC_MASK 3
+#define SB_CHAIN_SYNC_MASK 0  // measured: every step 45.37 ms, every 4th 45.61 ms at 2^19
 #endif
 
 enum fast_result : int {
@@ -262,7 +270,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
         if (dq != 0) {  // warp-uniform
             int idx = (dq < 0 ? -dq : dq) >> 1;
             if ((q_seen >> idx) & 1) {
-                exc |= jf_add(&Bq[idx], Dp, dq < 0 ? JOP_SUB : JOP_ADD);
+                exc |= jf_add<true>(&Bq[idx], Dp, dq < 0 ? JOP_SUB : JOP_ADD);
             } else {  // first digit of this bucket: a copy (warp-uniform, q is a constant)
                 Bq[idx] = *Dp;
                 if (dq < 0) Bq[idx].Y = fp6_neg(Bq[idx].Y);
@@ -273,10 +281,10 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             int dh = hd[j >> 2];
             int mag = dh < 0 ? -dh : dh;
             int idx = mag ? mag - 1 : 0;
-            exc |= jf_add(&Bh[idx], Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
+            exc |= jf_add<true>(&Bh[idx], Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
             if (mag) h_seen |= 1u << idx;
         }
-        if (j < 255) exc |= jf_dbl(Dp);
+        if (j < 255) exc |= jf_dbl<true>(Dp);
     }
     // Bucket aggregation (R_k = sum_{m>=k} B_m, O_k = sum_{m>=k} R_m):
     //   q (odd digits 2k+1):  [q]P = 2 O_1 + R_0        h (digits m = k+1):  h*P = O_0
@@ -290,27 +298,27 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     for (int b = 6; b >= 0; b--) {
         SB_PHASE_SYNC(1);
         bool eb = !((q_seen >> b) & 1);
-        exc |= jf_add(&Rq, &Bq[b], jf_add_mode(eRq, eb, false));
+        exc |= jf_add<true>(&Rq, &Bq[b], jf_add_mode(eRq, eb, false));
         eRq = eRq && eb;
         if (b >= 1) {
-            exc |= jf_add(&Oq, &Rq, jf_add_mode(eOq, eRq, false));
+            exc |= jf_add<true>(&Oq, &Rq, jf_add_mode(eOq, eRq, false));
             eOq = eOq && eRq;
         }
         eb = !((h_seen >> b) & 1);
-        exc |= jf_add(&Rh, &Bh[b], jf_add_mode(eRh, eb, false));
+        exc |= jf_add<true>(&Rh, &Bh[b], jf_add_mode(eRh, eb, false));
         if (!eb && !eRh) same_h = false;  // a real addition changed R
         eRh = eRh && eb;
         if (__builtin_expect(same_h && !eOh, 0)) {
-            exc |= jf_dbl(&Oh);           // O == R: O + R = 2 O
+            exc |= jf_dbl<true>(&Oh);           // O == R: O + R = 2 O
             same_h = false;
         } else {
-            exc |= jf_add(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
+            exc |= jf_add<true>(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
             same_h = eOh && !eRh;         // O was empty and has just been set to R
         }
         eOh = eOh && eRh;
     }
     if (eOq || eRq) exc = true;  // degenerate digit pattern: leave it to the exact routine
-    else exc |= jf_dbl(&Oq);
+    else exc |= jf_dbl<true>(&Oq);
     // [q]P = 2 O_1 + R_0 is the identity  <=>  2 O_1 == -R_0
     bool x_eq;
     bool torsion_free = jf_eq_neg(Oq, Rq, x_eq);
@@ -342,7 +350,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
                 T.Y.c[c] = ent[6 + c];
             }
 #endif
-            exc |= jf_add(R, &T, jf_add_mode(e_acc, dg == 0, neg));
+            exc |= jf_add<true>(R, &T, jf_add_mode(e_acc, dg == 0, neg));
             e_acc = e_acc && dg == 0;
         }
     }

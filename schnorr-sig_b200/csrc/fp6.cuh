@@ -92,6 +92,27 @@ SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) {
     }
 }
 
+// a * b - c * s with s in Fp (any 64-bit representative), c canonical: the scaled subtraction rides in the lazy
+// accumulators of the product -- six more 64x64 products, but no reduction and no subtraction of its own
+// (Y3 = L (A - X3) - Y s of the point formulas in affine.cuh)
+SB_DEV void fp6_mul_sub_scaled_body(fp6& r, const fp6& a, const fp6& b, const fp6& c, fp_t s) {
+    fp_t b7[6];
+#pragma unroll
+    for (int j = 1; j < 6; j++) b7[j] = fp_mul7_nc(b.c[j]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        wide_acc w;
+        wide_zero(w);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            if (i <= k) wide_mac(w, a.c[i], b.c[k - i]);
+            else wide_mac(w, a.c[i], b7[k + 6 - i]);
+        }
+        wide_mac(w, FP_P - c.c[k], s);
+        r.c[k] = wide_reduce(w);
+    }
+}
+
 #ifndef SB_FP6_INLINE
 #define SB_FP6_INLINE 0
 #endif
@@ -120,6 +141,11 @@ SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
     return r;
 }
 #endif
+SB_DEV_NOINLINE fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
+    fp6 r;
+    fp6_mul_sub_scaled_body(r, a, b, c, s);
+    return r;
+}
 
 // ---- cubic subfield Fp3 = Fp[v]/(v^3 - 7), v = u^2, used by inversion and square roots ----
 struct fp3 {
