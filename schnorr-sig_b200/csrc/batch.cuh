@@ -38,6 +38,14 @@ static msm_plan msm_make_plan(size_t npoints) {
             p.B = 1 << (c - 1);
         }
     }
+    if (const char* ov = getenv("SB_MSM_C")) {  // experiment knob: force the window width
+        int c = atoi(ov);
+        if (c >= 4 && c <= 16) {
+            p.c = c;
+            p.K = (256 + c - 1) / c;
+            p.B = 1 << (c - 1);
+        }
+    }
     // bucket-reduction chunks: aim at ~8k chunk threads in total (short serial chains), 8..32 buckets each
     int want = (int)(((double)p.B * p.K) / 8192.0);
     p.chunk_sz = want >= 32 ? 32 : (want >= 16 ? 16 : 8);
@@ -283,10 +291,12 @@ __global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restr
     else { store_jf_as_jac(&parts[2 * t + 1].pt, acc); parts[2 * t + 1].slot = (int32_t)s; }                     // tail
 }
 // one thread per slot: buckets that straddle segment boundaries are the sum of their partials
+static constexpr uint32_t MSM_LONG_SPAN = 16;  // segments; longer buckets go to k_msm_fixup_long
 __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t nslots, uint32_t T,
                                                            const uint32_t* __restrict__ offsets,
                                                            const uint32_t* __restrict__ counts,
-                                                           const seg_partial* __restrict__ parts, jac_pt* __restrict__ buckets) {
+                                                           const seg_partial* __restrict__ parts, jac_pt* __restrict__ buckets,
+                                                           uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     uint32_t cnt = counts[s];
@@ -294,6 +304,10 @@ __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t
     uint32_t beg = offsets[s], end = beg + cnt;
     uint32_t sa = beg / T, sb = (end - 1) / T;
     if (sa == sb) return;  // written directly by its segment
+    if (sb - sa >= MSM_LONG_SPAN) {  // a bucket spanning many segments (sparse top window, repeated randomisers,
+        long_list[atomicAdd(long_count, 1u)] = s;  // adversarial scalars): summed by a whole block, below
+        return;
+    }
     jf_pt acc = jf_identity();
     for (uint32_t g = sa; g <= sb; g++) {
 #pragma unroll 1
@@ -306,6 +320,53 @@ __global__ void __launch_bounds__(128) k_msm_segment_fixup(msm_plan pl, uint32_t
         }
     }
     store_jf_as_jac(&buckets[bucket_of_slot(pl, s)], acc);
+}
+
+// Buckets that span >= MSM_LONG_SPAN segments: one BLOCK per bucket.  The threads sum the partial records strided,
+// then a warp-shuffle tree and a last step through shared memory fold the 128 running sums -- a bucket holding a
+// quarter of all points (3-bit top window) costs ~25 serial additions instead of thousands.
+__device__ __forceinline__ jf_pt shfl_down_jf(const jf_pt& p, int delta);
+static constexpr int FIXUP_LONG_THREADS = 128;
+__global__ void __launch_bounds__(FIXUP_LONG_THREADS) k_msm_fixup_long(msm_plan pl, uint32_t T,
+                                                                      const uint32_t* __restrict__ offsets,
+                                                                      const uint32_t* __restrict__ counts,
+                                                                      const seg_partial* __restrict__ parts,
+                                                                      jac_pt* __restrict__ buckets,
+                                                                      const uint32_t* __restrict__ long_list,
+                                                                      const uint32_t* __restrict__ long_count) {
+    __shared__ jac_pt s_warp[FIXUP_LONG_THREADS / 32];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t li = blockIdx.x; li < *long_count; li += gridDim.x) {
+        uint32_t s = long_list[li];
+        uint32_t beg = offsets[s], end = beg + counts[s];
+        uint32_t sa = beg / T, sb = (end - 1) / T;
+        uint32_t np = 2 * (sb - sa + 1);  // head and tail record of every segment in range
+        jf_pt acc = jf_identity();
+        for (uint32_t r = threadIdx.x; r < np; r += FIXUP_LONG_THREADS) {
+            const seg_partial* p = &parts[2 * (size_t)sa + r];
+            if (p->slot == (int32_t)s) {
+                jf_pt t = load_jac_as_jf(&p->pt);
+                jf_add_exact(&acc, &t);
+            }
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            jf_pt o = shfl_down_jf(acc, d);
+            if (lane + d >= 32) o.w = 0;
+            jf_add_exact(&acc, &o);
+        }
+        if (lane == 0) store_jf_as_jac(&s_warp[warp], acc);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 1
+            for (int w = 1; w < FIXUP_LONG_THREADS / 32; w++) {
+                jf_pt t = load_jac_as_jf(&s_warp[w]);
+                jf_add_exact(&acc, &t);
+            }
+            store_jf_as_jac(&buckets[bucket_of_slot(pl, s)], acc);
+        }
+        __syncthreads();
+    }
 }
 
 // small multiple m * P (m >= 1) by double-and-add from the top set bit
@@ -500,10 +561,14 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     // segment length: 32 entries per thread, longer for very large batches (bounds the partial arrays)
     size_t max_entries = npts * (size_t)pl.K;
     uint32_t T = 32;
+    if (const char* ov = getenv("SB_MSM_T")) T = (uint32_t)atoi(ov) >= 8 ? (uint32_t)atoi(ov) : 32;  // experiment knob
     while ((max_entries + T - 1) / T > ((size_t)1 << 20)) T *= 2;
     size_t nseg = ((max_entries + T - 1) / T + 127) / 128 * 128;
     void* d_parts;
-    if (int rc = ensure_scratch(ctx, SL_I, nseg * 2 * sizeof(seg_partial), &d_parts)) return rc;
+    size_t max_long = nseg / MSM_LONG_SPAN + 1;  // buckets that can span >= MSM_LONG_SPAN segments
+    if (int rc = ensure_scratch(ctx, SL_I, nseg * 2 * sizeof(seg_partial) + 4 * max_long, &d_parts)) return rc;
+    uint32_t* long_list = (uint32_t*)((uint8_t*)d_parts + nseg * 2 * sizeof(seg_partial));
+    uint32_t* long_count = (uint32_t*)d_small + 1;  // zeroed with the `bad` flag below
     uint32_t* counts = (uint32_t*)d_cnt;
     uint32_t* offsets = counts + nslots;
     uint32_t* cursor = offsets + nslots;
@@ -532,11 +597,13 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
                                                               (uint32_t*)d_sorted, buckets, (seg_partial*)d_parts);
     cudaEventRecord(ctx->ev_k1, st);
     k_msm_segment_fixup<<<grid_for(nslots, 128), 128, 0, st>>>(pl, (uint32_t)nslots, T, offsets, counts,
-                                                               (seg_partial*)d_parts, buckets);
+                                                               (seg_partial*)d_parts, buckets, long_list, long_count);
+    k_msm_fixup_long<<<(unsigned)(max_long < 1024 ? max_long : 1024), FIXUP_LONG_THREADS, 0, st>>>(
+        pl, T, offsets, counts, (seg_partial*)d_parts, buckets, long_list, long_count);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, 64), 64, 0, st>>>(pl, buckets, chunk_out);
     k_msm_window_fold<<<pl.K, 32, 0, st>>>(pl, chunk_out, windows);
     k_msm_horner<<<1, 32, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
-    ctx->launches += 12;
+    ctx->launches += 13;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
 }
