@@ -114,6 +114,25 @@ def test_batch_with_skewed_randomisers_exercises_bucket_splitting():
     assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
 
 
+def test_batch_with_narrow_top_window_uses_the_block_fixup():
+    """Window widths whose top window has only 3 bits (c = 6, 12, 14: a handful of buckets hold an eighth of all
+    points each and span hundreds of segments -> k_msm_fixup_long) give the same points as the oracle."""
+    import os
+    import schnorr_sig_b200 as s
+    eng = s.default_engine(0)
+    n = 6000
+    w = make_workload(19, n, msg_len=8, nthreads=cref.default_threads())
+    cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"], cref.default_threads())
+    assert cv == 0
+    try:
+        for c in ("6", "12", "14", "9"):
+            os.environ["SB_MSM_C"] = c        # experiment knob of the host planner, read per call
+            v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"])
+            assert v == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr), c
+    finally:
+        os.environ.pop("SB_MSM_C", None)
+
+
 def test_mid_size_random_faults_against_oracle():
     """2^13 signatures with ragged messages and 1/16 injected faults: verdict vector equals the oracle's."""
     import schnorr_sig_b200 as s
