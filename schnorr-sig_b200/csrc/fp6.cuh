@@ -270,28 +270,35 @@ SB_DEV bool fp_is_square(fp_t a) {
     if (a == 0) return true;
     return fp_sqr_n(fp_pow_2_32_m1(a), 31) == 1;
 }
-// Tonelli-Shanks in Fp: p - 1 = 2^32 * (2^32 - 1).  Returns false if a is not a square.
+// Tonelli-Shanks in Fp with a WINDOWED discrete logarithm: p - 1 = 2^32 t, t = 2^32 - 1, g = 7^t generates the
+// 2-power torsion.  For a != 0: x = a^((t+1)/2), b = a^t = g^e, and sqrt(a) = x g^(-e/2) when e is even (a is a
+// non-residue when e is odd).  e is read eight bits at a time: (b g^-(e0 + ... ))^(2^(24-8i)) lies in the subgroup of
+// order 256, whose discrete log is one lookup in a perfect-hash table (include/fp_sqrt_tables.h, generated by
+// tools/gen_params.py).  48 squarings + 8 multiplications, uniform control flow -- the textbook loop needs ~300
+// squarings on average and diverges between the lanes of a warp.
+#if defined(__CUDACC__)
+#define FP_TABLE_QUAL __device__
+#endif
+}  // namespace sb
+#include "../../include/fp_sqrt_tables.h"
+namespace sb {
 static constexpr fp_t FP_NONE = ~0ULL;  // not a canonical element: "no square root"
 SB_DEV_NOINLINE fp_t fp_sqrt_or_none(fp_t a) {
     if (a == 0) return 0;
-    fp_t x = fp_sqr_n(a, 31);        // a^((t+1)/2), t = 2^32 - 1
-    fp_t b = fp_pow_2_32_m1(a);      // a^t
-    fp_t g = 0x185629dcda58878cULL;  // FP_ROOT_OF_UNITY_2_32 = 7^t (include/cheetah_params.h)
-    int r = 32;
-    while (b != 1) {
-        int m = 0;
-        fp_t bb = b;
-        while (bb != 1) {
-            bb = fp_sqr(bb);
-            if (++m == r) return FP_NONE;
-        }
-        fp_t gs = fp_sqr_n(g, r - m - 1);
-        g = fp_sqr(gs);
-        x = fp_mul(x, gs);
-        b = fp_mul(b, g);
-        r = m;
+    fp_t x = fp_sqr_n(a, 31);        // a^((t+1)/2)
+    fp_t c = fp_pow_2_32_m1(a);      // a^t, in the 2-power torsion
+    uint32_t e[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        fp_t bi = fp_sqr_n(c, 24 - 8 * i);  // order divides 256
+        e[i] = FP_SQRT_DLOG[(bi * FP_SQRT_DLOG_MUL) >> FP_SQRT_DLOG_SHIFT];
+        c = fp_mul(c, FP_SQRT_GINV[256 * i + e[i]]);
     }
-    return x;
+    if (e[0] & 1) return FP_NONE;
+    fp_t r = fp_mul(x, FP_SQRT_GINV[e[0] >> 1]);
+#pragma unroll
+    for (int i = 1; i < 4; i++) r = fp_mul(r, FP_SQRT_HALF[256 * (i - 1) + e[i]]);
+    return r;
 }
 SB_DEV bool fp_sqrt(fp_t a, fp_t& out) {
     fp_t r = fp_sqrt_or_none(a);

@@ -428,3 +428,21 @@ def test_exact_general_addition_in_fp_denominator_coordinates(hostsim):
         if a is not o.INF:
             assert run(a, o.pt_neg(a)) is o.INF and run(a, a, 3, 5) == o.pt_add(a, a)
     assert run(t2, t2) is o.INF
+
+
+def test_windowed_tonelli_shanks_in_fp(hostsim):
+    """fp_sqrt_or_none (windowed discrete log, include/fp_sqrt_tables.h): squares, non-residues, roots of unity."""
+    rng = np.random.default_rng(51)
+    g = pow(7, (o.P - 1) >> 32, o.P)                      # generator of the 2-power torsion
+    vals = [1, 4, o.P - 1, 2**32, 2**32 - 1, g, pow(g, 2, o.P), pow(g, 3, o.P), pow(g, 1 << 31, o.P), pow(g, (1 << 24) + 2, o.P),
+            pow(7, 12345, o.P), pow(7, 2 * 999983, o.P)] + [int(x) for x in rand_fp(rng, 300) if x]
+    r = C.c_uint64(0)
+    n_sq = 0
+    for a in vals:
+        is_sq = pow(a, (o.P - 1) // 2, o.P) == 1
+        ok = hostsim.hs_fp_sqrt(C.c_uint64(a), C.byref(r))
+        assert bool(ok) == is_sq, a
+        if is_sq:
+            assert r.value < o.P and r.value * r.value % o.P == a
+            n_sq += 1
+    assert 100 < n_sq < len(vals) - 100

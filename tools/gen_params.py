@@ -163,7 +163,43 @@ def main():
     os.makedirs(os.path.join(ROOT, "include"), exist_ok=True)
     with open(os.path.join(ROOT, "include", "cheetah_params.h"), "w") as f:
         f.write("".join(h))
-    print("wrote params/params.json and include/cheetah_params.h")
+
+    # ---- tables of the windowed Tonelli-Shanks square root in Fp (schnorr-sig_b200/csrc/fp6.cuh: fp_sqrt_or_none) ----
+    # p - 1 = 2^32 t, g = 7^t generates the 2-power torsion.  For a != 0: b = a^t = g^e; the discrete log e is read
+    # eight bits at a time from b^(2^24), (b g^-e0)^(2^16), ... in the order-256 subgroup (one table lookup each).
+    g = root32
+    ginv = pow(g, P - 2, P)
+    tab_ginv = [pow(ginv, j << (8 * i), P) for i in range(4) for j in range(256)]          # g^(-j 2^(8i))
+    tab_half = [pow(ginv, j << (8 * i - 1), P) for i in range(1, 4) for j in range(256)]   # g^(-j 2^(8i-1)), i = 1..3
+    g0 = pow(g, 1 << 24, P)                                                                 # order 256
+    mu = [pow(g0, j, P) for j in range(256)]
+    mult, bits = None, 12
+    cand = 0x9E3779B97F4A7C15
+    for _ in range(1 << 20):                     # multiplicative hash, injective on the 256 elements
+        if len({((v * cand) & (2**64 - 1)) >> (64 - bits) for v in mu}) == 256:
+            mult = cand
+            break
+        cand = (cand * 0xD1342543DE82EF95 + 1) & (2**64 - 1) | 1
+    assert mult is not None
+    dlog = [0] * (1 << bits)
+    for j, v in enumerate(mu):
+        dlog[((v * mult) & (2**64 - 1)) >> (64 - bits)] = j
+    t = []
+    t.append("/* GENERATED by tools/gen_params.py -- do not edit.  Tables of the windowed Tonelli-Shanks square root in the\n"
+             " * Goldilocks field (g = FP_ROOT_OF_UNITY_2_32).  Define FP_TABLE_QUAL (e.g. __device__) before including. */\n"
+             "#ifndef FP_SQRT_TABLES_H\n#define FP_SQRT_TABLES_H\n#include <stdint.h>\n#ifndef FP_TABLE_QUAL\n#define FP_TABLE_QUAL\n#endif\n\n")
+    t.append("#define FP_SQRT_DLOG_MUL 0x%016xULL   /* (v * MUL) >> %d is injective on the order-256 subgroup */\n" % (mult, 64 - bits))
+    t.append("#define FP_SQRT_DLOG_SHIFT %d\n\n" % (64 - bits))
+    t.append("/* g^(-j 2^(8i)), index 256 i + j */\n")
+    t.append(arr64("FP_SQRT_GINV", tab_ginv, 4).replace("static const", "FP_TABLE_QUAL static const"))
+    t.append("/* g^(-j 2^(8i-1)) for i = 1..3, index 256 (i-1) + j */\n")
+    t.append(arr64("FP_SQRT_HALF", tab_half, 4).replace("static const", "FP_TABLE_QUAL static const"))
+    t.append("/* discrete log base g^(2^24) of the order-256 subgroup, indexed by the multiplicative hash */\n")
+    t.append(arr8("FP_SQRT_DLOG", dlog, 32, "uint8_t").replace("static const", "FP_TABLE_QUAL static const"))
+    t.append("#endif /* FP_SQRT_TABLES_H */\n")
+    with open(os.path.join(ROOT, "include", "fp_sqrt_tables.h"), "w") as f:
+        f.write("".join(t))
+    print("wrote params/params.json, include/cheetah_params.h and include/fp_sqrt_tables.h")
 
 
 if __name__ == "__main__":
