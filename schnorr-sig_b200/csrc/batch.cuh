@@ -458,6 +458,41 @@ __device__ void jac_dbl_dist(fp_t& x, fp_t& y, fp_t& z, int g, int k) {
     x = X3;
     y = Y3;
 }
+// add-2007-bl on the same 24 lanes: (x1, y1, z1) += (x2, y2, z2), every value = the lane's coefficient k, replicated
+// over the four groups, which share the 16 products of the formula in five rounds.  Returns false (and leaves the
+// accumulator untouched) on the exceptional inputs -- an identity operand or equal x -- which the caller resolves
+// with the exact per-thread routine.
+__device__ bool jac_add_dist(fp_t& x1, fp_t& y1, fp_t& z1, fp_t x2, fp_t y2, fp_t z2, int g, int k) {
+    int gbase = 6 * g;
+    auto pick = [&](fp_t a, fp_t b, fp_t c, fp_t d) { return g == 0 ? a : (g == 1 ? b : (g == 2 ? c : d)); };
+    auto from = [&](fp_t v, int grp) { return shfl_fp(v, 6 * grp + k); };
+    auto all24 = [&](bool v) { return __ballot_sync(HORNER_MASK, v) == HORNER_MASK; };
+    if (all24(z1 == 0) || all24(z2 == 0)) return false;
+    // round 1: Z1Z1, Z2Z2, Y1 Z2, Y2 Z1
+    fp_t r1 = dfp6_mul(HORNER_MASK, pick(z1, z2, y1, y2), pick(z1, z2, z2, z1), k, gbase);
+    fp_t Z1Z1 = from(r1, 0), Z2Z2 = from(r1, 1), Y1Z2 = from(r1, 2), Y2Z1 = from(r1, 3);
+    // round 2: U1 = X1 Z2Z2, U2 = X2 Z1Z1, S1 = Y1 Z2 Z2Z2, S2 = Y2 Z1 Z1Z1
+    fp_t r2 = dfp6_mul(HORNER_MASK, pick(x1, x2, Y1Z2, Y2Z1), pick(Z2Z2, Z1Z1, Z2Z2, Z1Z1), k, gbase);
+    fp_t U1 = from(r2, 0), U2 = from(r2, 1), S1 = from(r2, 2), S2 = from(r2, 3);
+    fp_t H = fp_sub(U2, U1), rr = fp_dbl(fp_sub(S2, S1));
+    if (all24(H == 0)) return false;
+    // round 3: I = (2H)^2, (Z1 + Z2)^2
+    fp_t h2 = fp_dbl(H), zs = fp_add(z1, z2);
+    fp_t r3 = dfp6_mul(HORNER_MASK, (g & 1) ? zs : h2, (g & 1) ? zs : h2, k, gbase);
+    fp_t I = from(r3, 0), ZS = from(r3, 1);
+    // round 4: J = H I, V = U1 I, rr^2, Z3 = ((Z1+Z2)^2 - Z1Z1 - Z2Z2) H
+    fp_t zz = fp_sub(fp_sub(ZS, Z1Z1), Z2Z2);
+    fp_t r4 = dfp6_mul(HORNER_MASK, pick(H, U1, rr, zz), pick(I, I, rr, H), k, gbase);
+    fp_t J = from(r4, 0), V = from(r4, 1), RR = from(r4, 2), Z3 = from(r4, 3);
+    fp_t X3 = fp_sub(fp_sub(RR, J), fp_dbl(V));
+    // round 5: rr (V - X3), S1 J
+    fp_t r5 = dfp6_mul(HORNER_MASK, (g & 1) ? S1 : rr, (g & 1) ? J : fp_sub(V, X3), k, gbase);
+    fp_t Y3 = fp_sub(from(r5, 0), fp_dbl(from(r5, 1)));
+    x1 = X3;
+    y1 = Y3;
+    z1 = Z3;
+    return true;
+}
 // all coefficients of a distributed value, gathered from group 0
 __device__ __forceinline__ fp6 gather_fp6(fp_t v) {
     fp6 r;
@@ -472,17 +507,28 @@ __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, const jac_pt* __
     int lane = threadIdx.x;
     if (blockIdx.x != 0 || lane >= 24) return;
     int g = lane / 6, k = lane % 6;
-    jac_pt acc = windows[pl.K - 1];   // replicated on every lane between the doubling runs
+    // the accumulator stays distributed (lane k of every group holds coefficient k) across doublings and additions
+    fp_t x = windows[pl.K - 1].X.c[k], y = windows[pl.K - 1].Y.c[k], z = windows[pl.K - 1].Z.c[k];
 #pragma unroll 1
     for (int w = pl.K - 2; w >= 0; w--) {
-        fp_t x = acc.X.c[k], y = acc.Y.c[k], z = acc.Z.c[k];
 #pragma unroll 1
         for (int s = 0; s < pl.c; s++) jac_dbl_dist(x, y, z, g, k);
-        acc.X = gather_fp6(x);
-        acc.Y = gather_fp6(y);
-        acc.Z = gather_fp6(z);
-        jac_add_mem(&acc, &windows[w], false);  // all lanes redundantly (exceptional cases included)
+        if (!jac_add_dist(x, y, z, windows[w].X.c[k], windows[w].Y.c[k], windows[w].Z.c[k], g, k)) {
+            // identity operand or equal x (empty window, adversarial batch): the exact routine, all lanes redundantly
+            jac_pt acc;
+            acc.X = gather_fp6(x);
+            acc.Y = gather_fp6(y);
+            acc.Z = gather_fp6(z);
+            jac_add_mem(&acc, &windows[w], false);
+            x = acc.X.c[k];
+            y = acc.Y.c[k];
+            z = acc.Z.c[k];
+        }
     }
+    jac_pt acc;
+    acc.X = gather_fp6(x);
+    acc.Y = gather_fp6(y);
+    acc.Z = gather_fp6(z);
     if (lane != 0) return;
 #pragma unroll
     for (int c = 0; c < 6; c++) {
