@@ -60,12 +60,13 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
                                                        const uint64_t* __restrict__ msg_off,
                                                        const uint8_t* __restrict__ rand32, uint64_t* __restrict__ pts,
                                                        uint32_t* __restrict__ scalars, uint32_t* __restrict__ lin,
-                                                       int* __restrict__ bad) {
+                                                       int* __restrict__ bad, const uint32_t* __restrict__ h_in) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = in.n;
     bool live = i < n;
     uint64_t off = live ? msg_off[i] : 0, len = live ? msg_off[i + 1] - off : 0;
-    bool hash_sync = block_uniform_permutations(live ? hash_message_permutations(len) : -1);
+    // h_in != nullptr: the challenges were computed by k_batch_challenge_dist (small batches)
+    bool hash_sync = block_uniform_permutations(live && !h_in ? hash_message_permutations(len) : -1);
     if (!live) return;
     uint8_t fl = in.flags[i];
     fp6 sx = load_fp6_planes(in.planes, 0, n, i);
@@ -81,7 +82,13 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
     if (ok) ok = decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);  // unwrap panic, src/batch.rs:104
     // every live thread hashes (a malformed item's digest is simply unused): the permutation barriers stay matched,
     // and the barrier at its start re-aligns the warps after the divergent square-root loops
-    scalar h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
+    scalar h;
+    if (h_in) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) h.l[k] = h_in[i * 8 + k];
+    } else {
+        h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
+    }
     if (ok) {
         l = sc_mul(s, e);                     // src/batch.rs:92-97
         s_r = r_inf ? sc_zero() : s;          // identity contributes nothing
@@ -103,6 +110,35 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
         scalars[i * 8 + k] = s_r.l[k];
         scalars[(n + i) * 8 + k] = s_p.l[k];
         lin[i * 8 + k] = l.l[k];
+    }
+}
+
+// Challenges of a SMALL batch: one signature per group of six lanes (dist.cuh) -- the hash is two thirds of the serial
+// latency of k_batch_prepare, and a batch of a few thousand signatures cannot hide it behind other warps.
+__global__ void __launch_bounds__(DIST_THREADS) k_batch_challenge_dist(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                                       const uint64_t* __restrict__ msg_off,
+                                                                       uint32_t* __restrict__ h_out) {
+    __shared__ uint32_t s_mds2[24];
+    if (threadIdx.x < 24) s_mds2[threadIdx.x] = c_mds_row[threadIdx.x % 12];
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int g = lane / 6, k = lane % 6;
+    if (g >= 5) return;
+    size_t n = in.n;
+    size_t i = ((size_t)blockIdx.x * (DIST_THREADS / 32) + warp) * 5 + g;
+    if (i >= n) return;
+    int gbase = 6 * g;
+    unsigned mask = 0x3fu << gbase;
+    bool pk_inf = in.flags[i] & FL_PK_INF;  // the identity key hashes as x = y = 0 (challenge_scalar)
+    const uint64_t* pl = reinterpret_cast<const uint64_t*>(in.planes);
+    fp_t sx = pl[((size_t)(0 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    fp_t px = pk_inf ? 0 : pl[((size_t)(5 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    fp_t py = pk_inf ? 0 : pl[((size_t)(8 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    uint64_t off = msg_off[i];
+    scalar h = dchallenge_scalar(mask, sx, px, py, msgs + off, msg_off[i + 1] - off, k, gbase, s_mds2);
+    if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) h_out[i * 8 + j] = h.l[j];
     }
 }
 
@@ -670,7 +706,14 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, nslots * 4 * 3, st));
     CUDA_TRY(ctx, cudaMemsetAsync(d_small, 0, 64, st));
     k_ingest<<<grid_for(n, INGEST_THREADS), INGEST_THREADS, 0, st>>>(n, sigs81, pk96, pk_inf, soa);
-    k_batch_prepare<<<grid_for(n, 128), 128, 0, st>>>(soa, msgs, msg_off, rand32, (uint64_t*)d_pts, (uint32_t*)d_sc, lin, bad);
+    uint32_t* h_pre = nullptr;
+    if (n <= ctx->dist_max) {  // small batch: warp-cooperative challenges first (reuses the `sorted` buffer, written later)
+        h_pre = (uint32_t*)d_sorted;
+        k_batch_challenge_dist<<<grid_for(n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(soa, msgs, msg_off, h_pre);
+        ctx->launches += 1;
+    }
+    k_batch_prepare<<<grid_for(n, 128), 128, 0, st>>>(soa, msgs, msg_off, rand32, (uint64_t*)d_pts, (uint32_t*)d_sc, lin, bad,
+                                                      h_pre);
     int sum_blocks = (int)((n + 255) / 256);
     if (sum_blocks > 256) sum_blocks = 256;
     k_scalar_sum<<<sum_blocks, 256, 0, st>>>(lin, n, lin_part);
