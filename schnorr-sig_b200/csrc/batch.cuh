@@ -681,9 +681,11 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     if (int rc = ensure_scratch(ctx, SL_K, sizeof(jac_pt) * ((size_t)pl.K * pl.B + (size_t)pl.K * pl.chunks + pl.K), &d_buckets))
         return rc;
     if (int rc = ensure_scratch(ctx, SL_L, 64, &d_small)) return rc;
-    // segment length: 32 entries per thread, longer for very large batches (bounds the partial arrays)
+    // segment length: 8..32 entries per thread, longer for very large batches (bounds the partial arrays)
     size_t max_entries = npts * (size_t)pl.K;
+    // 8 (small batches: more, shorter chains -- the accumulation is latency-bound there) .. 32 entries per thread
     uint32_t T = 32;
+    while (T > 8 && max_entries / T < 65536) T /= 2;
     if (const char* ov = getenv("SB_MSM_T")) T = (uint32_t)atoi(ov) >= 8 ? (uint32_t)atoi(ov) : 32;  // experiment knob
     while ((max_entries + T - 1) / T > ((size_t)1 << 20)) T *= 2;
     size_t nseg = ((max_entries + T - 1) / T + 127) / 128 * 128;
