@@ -234,6 +234,12 @@ def test_verify_batch_points_bit_exact(eng, n):
     cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"], cref.default_threads())
     assert v == cv == 0
     assert np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+    eng.set_dist_threshold(0)                         # challenges hashed inside k_batch_prepare (the large-batch form)
+    try:
+        v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"])
+    finally:
+        eng.set_dist_threshold(10240)
+    assert v == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
     if n >= 5:
         pk2 = w["pk"].copy(); pk2[[1, 2]] = pk2[[2, 1]]
         v, lhs, rhs = eng.verify_batch(w["sigs"], pk2, w["inf"], w["blob"], w["off"], w["rand"])
