@@ -144,6 +144,22 @@ __device__ __noinline__ bool djf_add(unsigned mask, dpt* acc, const dpt* src, ui
     return wanted && n == 0;
 }
 
+// Exact forms for the reduction stages of the batch MSM (batch.cuh): the identity is w == 0; P + P and P - P are
+// resolved on a rarely taken, group-uniform branch (jf_add_exact / jf_dbl_exact of affine.cuh).
+__device__ __forceinline__ void djf_dbl_exact(unsigned mask, dpt* p, int k, int gbase) {
+    if (p->w == 0) return;
+    if (djf_dbl(mask, p, k, gbase)) p->w = 0;
+}
+__device__ __forceinline__ void djf_add_exact(unsigned mask, dpt* acc, const dpt* src, int k, int gbase) {
+    bool exc = djf_add(mask, acc, src, jf_add_mode(acc->w == 0, src->w == 0, false), k, gbase);
+    if (__builtin_expect(exc, 0)) {  // x(acc) == x(src): the same point (doubling) or opposite points (identity)
+        fp_t w1 = acc->w, w2 = src->w;
+        bool same = dall(mask, gbase,
+                         fp_mul(acc->Y, fp_mul_nc(fp_sqr_nc(w2), w2)) == fp_mul(src->Y, fp_mul_nc(fp_sqr_nc(w1), w1)));
+        if (!same || djf_dbl(mask, acc, k, gbase)) acc->w = 0;
+    }
+}
+
 // ---- Rescue-Prime with the state held two elements per lane: lane k has s[k] (lo) and s[k + 6] (hi) ----
 // y = M s + ark: every lane gathers the 12 inputs by shuffles and forms its two rows of the circulant matrix;
 // `mds2` = the MDS row twice (shared memory): M[i][j] = row[(j - i) mod 12] = mds2[j - i + 12]
