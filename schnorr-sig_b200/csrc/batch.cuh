@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(DIST_THREADS) k_msm_window_sum(msm_plan pl, co
     chunk_out[t].Y.c[kc] = acc.Y;
     chunk_out[t].Z.c[kc] = kc == 0 ? acc.w : 0;
 }
-// one warp per window: lanes add strided chunk results, then a shuffle tree ("warp-shuffle bucket reduction")
+// one block per window: threads add strided chunk results, then a shuffle tree ("warp-shuffle bucket reduction")
+// and a last step through shared memory
 __device__ __forceinline__ jf_pt shfl_down_jf(const jf_pt& p, int delta) {
     jf_pt r;
 #pragma unroll
@@ -453,21 +454,33 @@ __device__ __forceinline__ jf_pt shfl_down_jf(const jf_pt& p, int delta) {
     r.w = __shfl_down_sync(0xffffffffu, p.w, delta);
     return r;
 }
-__global__ void __launch_bounds__(32) k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out,
-                                                        jac_pt* __restrict__ windows) {
-    int k = blockIdx.x, lane = threadIdx.x;
+static constexpr int FOLD_THREADS = 128;
+__global__ void __launch_bounds__(FOLD_THREADS) k_msm_window_fold(msm_plan pl, const jac_pt* __restrict__ chunk_out,
+                                                                  jac_pt* __restrict__ windows) {
+    __shared__ jac_pt s_warp[FOLD_THREADS / 32];
+    int k = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     jf_pt acc = jf_identity();
 #pragma unroll 1
-    for (int ch = lane; ch < pl.chunks; ch += 32) {
+    for (int ch = threadIdx.x; ch < pl.chunks; ch += FOLD_THREADS) {
         jf_pt t = load_jac_as_jf(&chunk_out[(size_t)k * pl.chunks + ch]);
         jf_add_exact(&acc, &t);
     }
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         jf_pt o = shfl_down_jf(acc, d);
+        if (lane + d >= 32) o.w = 0;
         jf_add_exact(&acc, &o);
     }
-    if (lane == 0) store_jf_as_jac(&windows[k], acc);
+    if (lane == 0) store_jf_as_jac(&s_warp[warp], acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+        for (int w = 1; w < FOLD_THREADS / 32; w++) {
+            jf_pt t = load_jac_as_jf(&s_warp[w]);
+            jf_add_exact(&acc, &t);
+        }
+        store_jf_as_jac(&windows[k], acc);
+    }
 }
 // Horner over the windows is a serial chain of ~255 doublings, i.e. pure latency.  24 lanes of one warp share each
 // doubling on two levels:
@@ -736,7 +749,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     k_msm_fixup_long<<<(unsigned)(max_long < 1024 ? max_long : 1024), FIXUP_LONG_THREADS, 0, st>>>(
         pl, T, offsets, counts, (seg_partial*)d_parts, buckets, long_list, long_count);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(pl, buckets, chunk_out);
-    k_msm_window_fold<<<pl.K, 32, 0, st>>>(pl, chunk_out, windows);
+    k_msm_window_fold<<<pl.K, FOLD_THREADS, 0, st>>>(pl, chunk_out, windows);
     k_msm_horner<<<1, 32, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
     ctx->launches += 13;
     CUDA_TRY(ctx, cudaGetLastError());
