@@ -139,6 +139,13 @@ int schnorr_b200_compress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *pk96, 
 int schnorr_b200_debug_field_ops(schnorr_b200_ctx *ctx, size_t n, const uint64_t *a6, const uint64_t *b6,
                                  uint64_t *out48);
 
+/* Test hook (no reference counterpart): the lazily reduced building blocks of the fast path (csrc/debug_ops.cuh).
+ * a6: n x 6 ARBITRARY 64-bit limbs (non-canonical representatives allowed), b6: n x 6 canonical limbs; out48: n x 48
+ * u64 = a*rot(a) | a^2-2b | a^2-b-rot(b)*a3 | a*rot(a)-b*a5 | cofactor(b) | norm(b) | b*a0-rot(b)*a1 (nc form) |
+ * b*a0-rot(b)*a1, all canonicalised. */
+int schnorr_b200_debug_lazy_ops(schnorr_b200_ctx *ctx, size_t n, const uint64_t *a6, const uint64_t *b6,
+                                uint64_t *out48);
+
 /* Integer-multiply roofline calibration: runs a register-resident chain of `iters` dependent-free
  * 32x32->64 multiply-adds per thread on a full grid and returns wide multiplies per second. */
 int schnorr_b200_imad_peak(schnorr_b200_ctx *ctx, int iters, double *wide_mul_per_s, double *elapsed_ms);

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "schnorr_b200_decompress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
     "schnorr_b200_compress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
     "schnorr_b200_debug_field_ops": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p]),
+    "schnorr_b200_debug_lazy_ops": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p]),
     "schnorr_b200_imad_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

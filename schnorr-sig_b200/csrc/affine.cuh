@@ -32,15 +32,15 @@ SB_DEV void fp3_adj_norm_lazy(const fp3& d, fp3& adj, fp_t& norm) {
     wide_zero(w);
     wide_mac_sqr(w, d0);
     wide_mac(w, nd1, d2_7);
-    fp_t t0 = wide_reduce(w);
+    fp_t t0 = wide_reduce_nc(w);  // the adjugate only feeds products: any 64-bit representative will do
     wide_zero(w);
     wide_mac(w, d2, d2_7);
     wide_mac(w, nd0, d1);
-    fp_t t1 = wide_reduce(w);
+    fp_t t1 = wide_reduce_nc(w);
     wide_zero(w);
     wide_mac_sqr(w, d1);
     wide_mac(w, nd0, d2);
-    fp_t t2 = wide_reduce(w);
+    fp_t t2 = wide_reduce_nc(w);
     wide_zero(w);
     wide_mac(w, d0, t0);
     wide_mac(w, d2_7, t1);
@@ -62,7 +62,8 @@ struct jf_pt {
     fp_t w;
 };
 
-// a * b in Fp3 with the wrap-around multiples 7 b1, 7 b2 supplied by the caller (shared by several products)
+// a * b in Fp3 with the wrap-around multiples 7 b1, 7 b2 supplied by the caller (shared by several products);
+// coefficients returned as arbitrary 64-bit representatives (the cofactor only feeds a multiplication)
 SB_DEV fp3 fp3_mul_pre(const fp3& a, const fp3& b, fp_t b7_1, fp_t b7_2) {
     fp3 r;
     wide_acc w;
@@ -70,31 +71,58 @@ SB_DEV fp3 fp3_mul_pre(const fp3& a, const fp3& b, fp_t b7_1, fp_t b7_2) {
     wide_mac(w, a.c[0], b.c[0]);
     wide_mac(w, a.c[1], b7_2);
     wide_mac(w, a.c[2], b7_1);
-    r.c[0] = wide_reduce(w);
+    r.c[0] = wide_reduce_nc(w);
     wide_zero(w);
     wide_mac(w, a.c[0], b.c[1]);
     wide_mac(w, a.c[1], b.c[0]);
     wide_mac(w, a.c[2], b7_2);
-    r.c[1] = wide_reduce(w);
+    r.c[1] = wide_reduce_nc(w);
     wide_zero(w);
     wide_mac(w, a.c[0], b.c[2]);
     wide_mac(w, a.c[1], b.c[1]);
     wide_mac(w, a.c[2], b.c[0]);
-    r.c[2] = wide_reduce(w);
+    r.c[2] = wide_reduce_nc(w);
     return r;
 }
 
-// d * c = n,  c in Fp6, n in Fp;  n == 0 <=> d == 0
+// d * c = n,  c in Fp6 (coefficients NOT canonical: c only ever feeds a multiplication), n in Fp canonical;
+// n == 0 <=> d == 0.  d canonical.
+//   d = x + y u over Fp3 (x = (d0, d2, d4), y = (d1, d3, d5)),  1/d = (x - y u) / N,  N = x^2 - v y^2 in Fp3,
+//   v (t0, t1, t2) = (7 t2, t0, t1).  The three coefficients of N are accumulated directly (12 products, three
+//   reductions, no subtraction: the y terms enter through p - y_i):
+//     N0 = x0^2 + 2 x1 7x2 - 2 y0 7y2 - y1 7y1      N1 = 2 x0 x1 + x2 7x2 - y0^2 - 2 y1 7y2
+//     N2 = 2 x0 x2 + x1^2 - 2 y0 y1 - y2 7y2
 SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
-    fp3 a0, a1, adj;
-    fp6_split(*d, a0, a1);
-    fp3 s0 = fp3_sqr6(a0), s1 = fp3_sqr6(a1);
-    // N = a0^2 - v a1^2 in Fp3,  v (x0, x1, x2) = (7 x2, x0, x1);   1/d = (a0 - a1 u) / N
-    fp3 nn = fp3{{fp_sub(s0.c[0], fp_mul7(s1.c[2])), fp_sub(s0.c[1], s1.c[0]), fp_sub(s0.c[2], s1.c[1])}};
+    fp3 x, y, adj;
+    fp6_split(*d, x, y);
+    fp3 ny = fp3{{FP_P - y.c[0], FP_P - y.c[1], FP_P - y.c[2]}};
+    fp_t x2_7 = fp_mul7_nc(x.c[2]), y1_7 = fp_mul7_nc(y.c[1]), y2_7 = fp_mul7_nc(y.c[2]);
+    fp3 nn;
+    wide_acc w;
+    wide_zero(w);
+    wide_mac(w, x.c[1], x2_7);
+    wide_mac(w, ny.c[0], y2_7);
+    wide_double(w);
+    wide_mac_sqr(w, x.c[0]);
+    wide_mac(w, ny.c[1], y1_7);
+    nn.c[0] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, x.c[0], x.c[1]);
+    wide_mac(w, ny.c[1], y2_7);
+    wide_double(w);
+    wide_mac(w, x.c[2], x2_7);
+    wide_mac(w, ny.c[0], y.c[0]);
+    nn.c[1] = wide_reduce(w);
+    wide_zero(w);
+    wide_mac(w, x.c[0], x.c[2]);
+    wide_mac(w, ny.c[0], y.c[1]);
+    wide_double(w);
+    wide_mac_sqr(w, x.c[1]);
+    wide_mac(w, ny.c[2], y2_7);
+    nn.c[2] = wide_reduce(w);
     fp3_adj_norm_lazy(nn, adj, *n);  // 1/N = adj / n
-    fp3 na1 = fp3{{FP_P - a1.c[0], FP_P - a1.c[1], FP_P - a1.c[2]}};
     fp_t adj7_1 = fp_mul7_nc(adj.c[1]), adj7_2 = fp_mul7_nc(adj.c[2]);
-    *c = fp6_join(fp3_mul_pre(a0, adj, adj7_1, adj7_2), fp3_mul_pre(na1, adj, adj7_1, adj7_2));
+    *c = fp6_join(fp3_mul_pre(x, adj, adj7_1, adj7_2), fp3_mul_pre(ny, adj, adj7_1, adj7_2));
 }
 
 // a * s for s in Fp (any 64-bit representative)
@@ -126,9 +154,24 @@ SB_SCALE_FN fp6 fp6_scale_diff(fp6 a, fp_t s, fp6 b, fp_t t) {
     return r;
 }
 
+// a * s - b * t with non-canonical coefficients (feeds a multiplication only)
+SB_SCALE_FN fp6 fp6_scale_diff_nc(fp6 a, fp_t s, fp6 nb, fp_t t) {  // nb = a representative of -b (p - b, or b itself
+    fp6 r;                                                          // when the caller wants a s + b t)
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        wide_acc w;
+        wide_zero(w);
+        wide_mac(w, a.c[i], s);
+        wide_mac(w, nb.c[i], t);
+        r.c[i] = wide_reduce_nc(w);
+    }
+    return r;
+}
+
 // p <- 2 p.  Returns true on the exceptional input (a point of order 2: the result would be the identity).
-// FUSED: Y3 through fp6_mul_sub_scaled (1 % faster in k_verify_fast, but its 38 argument registers cost
-// k_msm_segment_sum a resident block -> the MSM kernels use the plain form)
+// FUSED (k_verify_fast): X3 = L^2 - 2 A and Y3 = L (A - X3) - Y m^3 each come out of ONE lazy accumulation
+// (fp6_sqr_sub2, fp6_mul_sub_scaled), L and the cofactor stay non-canonical.  The MSM kernels keep the plain
+// form: the fused helpers take 38 argument registers, which costs k_msm_segment_sum a resident block.
 template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     fp6 X = p->X, Y = p->Y, c;
@@ -139,13 +182,18 @@ SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     fp6 xx = fp6_sqr(X);
     fp6 num = fp6_add(fp6_dbl(xx), xx);
     num.c[0] = fp_add(num.c[0], w4);        // 3 X^2 + a w^4, a = 1
-    fp6 L = fp6_mul(num, c);                // slope = L / (m w)
     fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
     fp6 A = fp6_scale(X, m2);
-    fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
-    fp6 Y3;
-    if (FUSED) Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
-    else Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
+    fp6 X3, Y3;
+    if (FUSED) {
+        fp6 L = fp6_mul_nc(num, c);         // slope = L / (m w)
+        X3 = fp6_sqr_sub2(L, A);
+        Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
+    } else {
+        fp6 L = fp6_mul(num, c);
+        X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
+        Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
+    }
     p->X = X3;
     p->Y = Y3;
     p->w = fp_mul(m, w);
@@ -170,25 +218,49 @@ template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
     fp6 X1 = acc->X, Y1 = acc->Y, X2 = src->X, Y2 = src->Y;
     fp_t w1 = acc->w, w2 = src->w;
-    if (mode == JOP_SUB || mode == JOP_SETNEG) Y2 = fp6_neg(Y2);
+    bool negate = mode == JOP_SUB || mode == JOP_SETNEG;
     fp_t w1s = fp_sqr_nc(w1), w1c = fp_mul_nc(w1s, w1), w2s = fp_sqr_nc(w2), w2c = fp_mul_nc(w2s, w2);
     fp6 d = fp6_scale_diff(X1, w2s, X2, w1s);    // U1 - U2,  U1 = X1 w2^2,  U2 = X2 w1^2
-    fp6 num = fp6_scale_diff(Y1, w2c, Y2, w1c);  // S1 - S2
     fp6 c;
     fp_t n;
+    bool wanted = mode == JOP_ADD || mode == JOP_SUB;
+    bool set = mode == JOP_SET || mode == JOP_SETNEG;
+    if (FUSED) {
+        // S1 - (+|-) S2: the sign of src enters through the representative of -Y2 handed to the accumulation
+        fp6 nY2;
+#pragma unroll
+        for (int i = 0; i < 6; i++) nY2.c[i] = negate ? Y2.c[i] : FP_P - Y2.c[i];
+        fp6 num = fp6_scale_diff_nc(Y1, w2c, nY2, w1c);
+        fp6_cofactor_norm(&d, &c, &n);
+        fp6 L = fp6_mul_nc(num, c);                  // slope = L / (n w1 w2)
+        fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
+        fp6 A = fp6_scale(X1, fp_mul_nc(n2, w2s));   // n^2 U1 = x1 w3^2
+        fp6 X3 = fp6_sqr_sub_scaled(L, A, X2, fp_mul_nc(n2, w1s));            // L^2 - x1 w3^2 - x2 w3^2
+        fp6 Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y1, fp_mul_nc(n3, w2c));  // L (x1 w3^2 - X3) - y1 w3^3
+        fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
+        if (wanted && n != 0) {  // on the exceptional input acc is left untouched
+            acc->X = X3;
+            acc->Y = Y3;
+            acc->w = w3;
+        } else if (set) {
+            acc->X = X2;
+#pragma unroll
+            for (int i = 0; i < 6; i++) acc->Y.c[i] = negate ? fp_neg(Y2.c[i]) : Y2.c[i];
+            acc->w = w2;
+        }
+        return wanted && n == 0;
+    }
+    if (negate) Y2 = fp6_neg(Y2);
+    fp6 num = fp6_scale_diff(Y1, w2c, Y2, w1c);  // S1 - S2
     fp6_cofactor_norm(&d, &c, &n);
     fp6 L = fp6_mul(num, c);                     // slope = L / (n w1 w2)
     fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
     fp6 A = fp6_scale(X1, fp_mul_nc(n2, w2s));   // n^2 U1 = x1 w3^2
     fp6 B = fp6_scale(X2, fp_mul_nc(n2, w1s));   // n^2 U2 = x2 w3^2
     fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), B);
-    fp6 Y3;                                      // L (x1 w3^2 - X3) - y1 w3^3
-    if (FUSED) Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y1, fp_mul_nc(n3, w2c));
-    else Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));
+    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y1, fp_mul_nc(n3, w2c)));  // L (x1 w3^2 - X3) - y1 w3^3
     fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
-    bool wanted = mode == JOP_ADD || mode == JOP_SUB;
     bool active = wanted && n != 0;  // on the exceptional input acc is left untouched
-    bool set = mode == JOP_SET || mode == JOP_SETNEG;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         acc->X.c[i] = active ? X3.c[i] : (set ? X2.c[i] : X1.c[i]);

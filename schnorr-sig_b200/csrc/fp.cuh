@@ -62,8 +62,12 @@ SB_DEV fp_t fp_add(fp_t a, fp_t b) { return fp_sub(a, FP_P - b); }
 SB_DEV fp_t fp_neg(fp_t a) { return a ? FP_P - a : 0; }
 SB_DEV fp_t fp_dbl(fp_t a) { return fp_add(a, a); }
 
-// x = x0 + x1*2^32 + x2*2^64 (x2 < 2^32)  ->  canonical x mod p:   x = (x1:x0) + x2*(2^32-1)
-SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
+// x = x0 + x1*2^32 + x2*2^64 (x2 < 2^32)  ->  x mod p as ANY 64-bit representative ("nc": may be >= p):
+//   x = (x1:x0) + x2*(2^32-1)
+// Every consumer that only multiplies (wide_mac, fp_mul_nc, ...) or uses the value as the MINUEND of fp_sub accepts
+// this form; the canonicalisation below costs 4 more instructions and is only paid where a value is compared,
+// stored, negated (p - x) or subtracted.
+SB_DEV fp_t fp_reduce96_nc(uint32_t x0, uint32_t x1, uint32_t x2) {
 #if defined(__CUDA_ARCH__)
     uint32_t t0, t1;
     asm("{\n\t"
@@ -79,25 +83,36 @@ SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(x0), "r"(x1), "r"(x2));
-    bool ge = (t1 == 0xffffffffu) & (t0 != 0);  // t >= p  <=>  high word all ones and low word >= 1
-    t1 = ge ? 0u : t1;
-    t0 -= ge ? 1u : 0u;
     return ((uint64_t)t1 << 32) | t0;
 #else
     uint64_t t = ((uint64_t)x1 << 32) | x0;
     uint64_t m = ((uint64_t)x2 << 32) - x2;
     uint64_t r = t + m;
     if (r < m) r += FP_EPS;  // r <= 2^64 - 2^33 after the wrap: cannot overflow again
+    return r;
+#endif
+}
+// ... -> canonical x mod p
+SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
+    fp_t r = fp_reduce96_nc(x0, x1, x2);
+#if defined(__CUDA_ARCH__)
+    uint32_t t0 = (uint32_t)r, t1 = (uint32_t)(r >> 32);
+    bool ge = (t1 == 0xffffffffu) & (t0 != 0);  // t >= p  <=>  high word all ones and low word >= 1
+    t1 = ge ? 0u : t1;
+    t0 -= ge ? 1u : 0u;
+    return ((uint64_t)t1 << 32) | t0;
+#else
     if (r >= FP_P) r -= FP_P;
     return r;
 #endif
 }
 
-// x = x0 + x1*2^32 + x2*2^64 + x3*2^96 + x4*2^128  ->  canonical x mod p
+// x = x0 + x1*2^32 + x2*2^64 + x3*2^96 + x4*2^128  ->  x mod p
 // using 2^64 = 2^32-1, 2^96 = -1, 2^128 = -2^32 (mod p):
 //   x = (x0 + x1*2^32) - (x3 + x4*2^32) + x2*(2^32-1)
 // x4 must be small (< 2^31): it only ever holds the carries of a dot product.
-SB_DEV fp_t fp_reduce160(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
+template <bool CANON>
+SB_DEV fp_t fp_reduce160_t(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
 #if defined(__CUDA_ARCH__)
     uint32_t t0, t1;
     asm("{\n\t"
@@ -110,14 +125,17 @@ SB_DEV fp_t fp_reduce160(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uin
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(x0), "r"(x1), "r"(x3), "r"(x4));
-    return fp_reduce96(t0, t1, x2);
+    return CANON ? fp_reduce96(t0, t1, x2) : fp_reduce96_nc(t0, t1, x2);
 #else
     uint64_t lo = ((uint64_t)x1 << 32) | x0;
     uint64_t sub = ((uint64_t)x4 << 32) | x3;
     uint64_t t = lo - sub;
     if (lo < sub) t -= FP_EPS;  // t >= 2^64 - sub >> EPS: no second borrow
-    return fp_reduce96((uint32_t)t, (uint32_t)(t >> 32), x2);
+    return CANON ? fp_reduce96((uint32_t)t, (uint32_t)(t >> 32), x2) : fp_reduce96_nc((uint32_t)t, (uint32_t)(t >> 32), x2);
 #endif
+}
+SB_DEV fp_t fp_reduce160(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
+    return fp_reduce160_t<true>(x0, x1, x2, x3, x4);
 }
 
 // Lazy accumulator of a sum of 64x64-bit products: value = E + O * 2^32
@@ -202,7 +220,8 @@ SB_DEV void wide_double(wide_acc& w) {
     w.o1 <<= 1;
 }
 
-SB_DEV fp_t wide_reduce(const wide_acc& w) {
+template <bool CANON>
+SB_DEV fp_t wide_reduce_t(const wide_acc& w) {
     uint32_t x1, x2, x3, x4;
 #if defined(__CUDA_ARCH__)
     asm("add.cc.u32 %0, %4, %8;\n\t"
@@ -219,7 +238,30 @@ SB_DEV fp_t wide_reduce(const wide_acc& w) {
     x3 = (uint32_t)(hi >> 64);
     x4 = (uint32_t)(hi >> 96);
 #endif
-    return fp_reduce160(w.e0, x1, x2, x3, x4);
+    return fp_reduce160_t<CANON>(w.e0, x1, x2, x3, x4);
+}
+SB_DEV fp_t wide_reduce(const wide_acc& w) { return wide_reduce_t<true>(w); }
+// any 64-bit representative of the accumulated value (see fp_reduce96_nc)
+SB_DEV fp_t wide_reduce_nc(const wide_acc& w) { return wide_reduce_t<false>(w); }
+
+// w = v (start an accumulation from a 64-bit value instead of zero: a free addition)
+SB_DEV void wide_set64(wide_acc& w, uint64_t v) { w = wide_acc{(uint32_t)v, (uint32_t)(v >> 32), 0, 0, 0, 0, 0, 0}; }
+// w += v for a 64-bit value v
+SB_DEV void wide_add64(wide_acc& w, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(w.e0), "+r"(w.e1), "+r"(w.e2), "+r"(w.e3), "+r"(w.e4)
+        : "r"((uint32_t)v), "r"((uint32_t)(v >> 32)));
+#else
+    unsigned __int128 lo = ((unsigned __int128)w.e3 << 96) | ((unsigned __int128)w.e2 << 64) | ((uint64_t)w.e1 << 32) | w.e0;
+    unsigned __int128 s = lo + v;
+    if (s < lo) w.e4++;
+    w.e0 = (uint32_t)s; w.e1 = (uint32_t)(s >> 32); w.e2 = (uint32_t)(s >> 64); w.e3 = (uint32_t)(s >> 96);
+#endif
 }
 
 // ---- single products -----------------------------------------------------------------------------

@@ -49,6 +49,9 @@ SB_DEV bool fp6_is_canonical(const fp6& a) {
     return ok;
 }
 
+// CANON = false: the coefficients are returned as arbitrary 64-bit representatives (fp_reduce96_nc) -- for
+// products that only feed further multiplications
+template <bool CANON = true>
 SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
     fp_t b7[6];
 #pragma unroll
@@ -62,18 +65,25 @@ SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
             if (i <= k) wide_mac(w, a.c[i], b.c[k - i]);
             else wide_mac(w, a.c[i], b7[k + 6 - i]);
         }
-        r.c[k] = wide_reduce(w);
+        r.c[k] = wide_reduce_t<CANON>(w);
     }
 }
 
-SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) {
+// Squaring with optional subtracted terms riding in the lazy accumulators (no reduction / subtraction of their own):
+//   MODE 0:  a^2
+//   MODE 1:  a^2 - 2 A              (A canonical; p - A_k starts the accumulator and is doubled with the cross terms)
+//   MODE 2:  a^2 - A - B s          (A, B canonical; s any 64-bit representative of an Fp element)
+// These are X3 = L^2 - 2 X m^2 and X3 = L^2 - x1 w3^2 - x2 w3^2 of the point formulas in affine.cuh.
+template <int MODE>
+SB_DEV void fp6_sqr_body_t(fp6& r, const fp6& a, const fp6* A, const fp6* B, fp_t s) {
     fp_t a7[6];
 #pragma unroll
     for (int j = 3; j < 6; j++) a7[j] = fp_mul7_nc(a.c[j]);
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         wide_acc w;
-        wide_zero(w);
+        if (MODE == 1) wide_set64(w, FP_P - A->c[k]);
+        else wide_zero(w);
         // cross terms i < j
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -88,9 +98,14 @@ SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) {
             wide_mac_sqr(w, a.c[k / 2]);
             wide_mac(w, a.c[k / 2 + 3], a7[k / 2 + 3]);
         }
+        if (MODE == 2) {
+            wide_add64(w, FP_P - A->c[k]);
+            wide_mac(w, FP_P - B->c[k], s);
+        }
         r.c[k] = wide_reduce(w);
     }
 }
+SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) { fp6_sqr_body_t<0>(r, a, nullptr, nullptr, 0); }
 
 // a * b - c * s with s in Fp (any 64-bit representative), c canonical: the scaled subtraction rides in the lazy
 // accumulators of the product -- six more 64x64 products, but no reduction and no subtraction of its own
@@ -119,7 +134,7 @@ SB_DEV void fp6_mul_sub_scaled_body(fp6& r, const fp6& a, const fp6& b, const fp
 #if SB_FP6_INLINE
 SB_DEV fp6 fp6_mul(const fp6& a, const fp6& b) {
     fp6 r;
-    fp6_mul_body(r, a, b);
+    fp6_mul_body<true>(r, a, b);
     return r;
 }
 SB_DEV fp6 fp6_sqr(const fp6& a) {
@@ -132,7 +147,7 @@ SB_DEV fp6 fp6_sqr(const fp6& a) {
 // instruction cache.
 SB_DEV_NOINLINE fp6 fp6_mul(fp6 a, fp6 b) {
     fp6 r;
-    fp6_mul_body(r, a, b);
+    fp6_mul_body<true>(r, a, b);
     return r;
 }
 SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
@@ -144,6 +159,24 @@ SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
 SB_DEV_NOINLINE fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
     fp6 r;
     fp6_mul_sub_scaled_body(r, a, b, c, s);
+    return r;
+}
+// a * b with non-canonical coefficients (feeds multiplications only)
+SB_DEV_NOINLINE fp6 fp6_mul_nc(fp6 a, fp6 b) {
+    fp6 r;
+    fp6_mul_body<false>(r, a, b);
+    return r;
+}
+// a^2 - 2 A
+SB_DEV_NOINLINE fp6 fp6_sqr_sub2(fp6 a, fp6 A) {
+    fp6 r;
+    fp6_sqr_body_t<1>(r, a, &A, nullptr, 0);
+    return r;
+}
+// a^2 - A - B s
+SB_DEV_NOINLINE fp6 fp6_sqr_sub_scaled(fp6 a, fp6 A, fp6 B, fp_t s) {
+    fp6 r;
+    fp6_sqr_body_t<2>(r, a, &A, &B, s);
     return r;
 }
 

@@ -21,6 +21,7 @@
 #include "../../include/schnorr_b200.h"
 #include "verify.cuh"
 #include "dist.cuh"
+#include "debug_ops.cuh"
 
 using namespace sb;
 
@@ -568,6 +569,22 @@ __global__ void __launch_bounds__(128) k_debug_field(size_t n, const uint64_t* _
     }
 }
 
+// test hook for the lazily reduced forms of the fast path (debug_ops.cuh): out[i] = 8 x 6 limbs
+__global__ void __launch_bounds__(128) k_debug_lazy(size_t n, const uint64_t* __restrict__ a6, const uint64_t* __restrict__ b6,
+                                                    uint64_t* __restrict__ out48) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp6 a, b, r[8];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        a.c[k] = a6[i * 6 + k];
+        b.c[k] = b6[i * 6 + k];
+    }
+    debug_lazy_ops(a, b, r);
+    for (int j = 0; j < 8; j++)
+        for (int k = 0; k < 6; k++) out48[i * 48 + 6 * j + k] = r[j].c[k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K6: integer-multiply roofline calibration.  8 independent accumulator chains per thread of
 // 32x32+64 -> 64 multiply-adds (IMAD.WIDE.U32), no memory traffic.
@@ -1043,6 +1060,22 @@ int schnorr_b200_debug_field_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t
     if (int rc = stage_in(ctx, SL_E, b6, n * 48, &d_b)) return rc;
     if (int rc = ensure_scratch(ctx, SL_H, n * 48 * 8, &d_o)) return rc;
     k_debug_field<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint64_t*)d_a, (uint64_t*)d_b, (uint64_t*)d_o);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out48, d_o, n * 48 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+int schnorr_b200_debug_lazy_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t* a6, const uint64_t* b6, uint64_t* out48) {
+    if (!ctx || (n && (!a6 || !b6 || !out48))) return SCHNORR_B200_EARG;
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_a, *d_b, *d_o;
+    if (int rc = stage_in(ctx, SL_D, a6, n * 48, &d_a)) return rc;
+    if (int rc = stage_in(ctx, SL_E, b6, n * 48, &d_b)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_H, n * 48 * 8, &d_o)) return rc;
+    k_debug_lazy<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint64_t*)d_a, (uint64_t*)d_b, (uint64_t*)d_o);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out48, d_o, n * 48 * 8, cudaMemcpyDeviceToHost, ctx->stream));

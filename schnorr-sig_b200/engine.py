@@ -233,6 +233,14 @@ class Engine:
         self._check(self._L.schnorr_b200_debug_field_ops(self._h, a6.shape[0], _ptr(a6), _ptr(b6), _ptr(out)), "debug_field_ops")
         return out
 
+    def debug_lazy_ops(self, a6, b6):
+        """Test hook: lazily reduced fast-path building blocks (a6 may hold non-canonical limbs) -> [n, 8, 6] uint64."""
+        a6 = np.ascontiguousarray(a6, dtype=np.uint64).reshape(-1, 6)
+        b6 = np.ascontiguousarray(b6, dtype=np.uint64).reshape(-1, 6)
+        out = np.zeros((a6.shape[0], 8, 6), dtype=np.uint64)
+        self._check(self._L.schnorr_b200_debug_lazy_ops(self._h, a6.shape[0], _ptr(a6), _ptr(b6), _ptr(out)), "debug_lazy_ops")
+        return out
+
     def imad_peak(self, iters=1 << 16):
         w = C.c_double(0)
         ms = C.c_double(0)

@@ -10,6 +10,7 @@
 
 #include "../../include/cheetah_params.h"
 #include "../../schnorr-sig_b200/csrc/verify.cuh"
+#include "../../schnorr-sig_b200/csrc/debug_ops.cuh"
 
 using namespace sb;
 
@@ -242,12 +243,32 @@ API int hs_jf_dbl(const uint8_t* a96, uint64_t wa, uint8_t* out96) {
     if (!exc) jf_to_affine(a, out96);
     return exc;
 }
+// the fused forms k_verify_fast instantiates (lazy accumulations, non-canonical intermediates)
+API int hs_jf_add_fused(const uint8_t* a96, uint64_t wa, const uint8_t* b96, uint64_t wb, int mode, uint8_t* out96) {
+    jf_pt a = jf_from_affine(a96, wa), b = jf_from_affine(b96, wb);
+    bool exc = jf_add<true>(&a, &b, (uint8_t)mode);
+    jf_to_affine(a, out96);
+    return exc;
+}
+API int hs_jf_dbl_fused(const uint8_t* a96, uint64_t wa, uint8_t* out96) {
+    jf_pt a = jf_from_affine(a96, wa);
+    bool exc = jf_dbl<true>(&a);
+    if (!exc) jf_to_affine(a, out96);
+    return exc;
+}
 API uint64_t hs_fp6_cofactor_norm(const uint64_t* d, uint64_t* c) {
     fp6 dd = ld6(d), cc;
     fp_t n;
     fp6_cofactor_norm(&dd, &cc, &n);
     st6(c, cc);
     return n;
+}
+
+// lazily reduced building blocks on raw limbs (a may be non-canonical): out = 8 x 6 limbs (debug_ops.cuh)
+API void hs_debug_lazy_ops(const uint64_t* a, const uint64_t* b, uint64_t* out48) {
+    fp6 r[8];
+    debug_lazy_ops(ld6(a), ld6(b), r);
+    for (int j = 0; j < 8; j++) st6(out48 + 6 * j, r[j]);
 }
 
 // 32x32->64 multiplies executed since the last call (cost figures of DESIGN.md; test-only counter in fp.cuh)

@@ -344,20 +344,22 @@ def test_fp_denominator_jacobian_operations(hostsim):
     ws = [1, 2, o.P - 1, 0x123456789abcdef] + [int(x) for x in rand_fp(rng, 3)]
     out = np.zeros(96, dtype=np.uint8)
     NOP, ADD, SUB, SET, SETNEG = 0, 1, 2, 3, 4
-    for i, a in enumerate(pts):
-        wa, wb = ws[i % len(ws)], ws[(3 * i + 1) % len(ws)]
-        b = pts[(i + 2) % len(pts)]
-        A, B = pt_to96(a), pt_to96(b)
-        assert hostsim.hs_jf_dbl(p(A), C.c_uint64(wa), p(out)) == 0 and pt_from96(out) == o.pt_add(a, a)
-        for mode, want in ((ADD, o.pt_add(a, b)), (SUB, o.pt_add(a, o.pt_neg(b))), (SET, b), (SETNEG, o.pt_neg(b)), (NOP, a)):
-            assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(B), C.c_uint64(wb), mode, p(out)) == 0
-            assert pt_from96(out) == want, (i, mode)
-        # exceptional inputs are reported when active, ignored when masked
-        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), ADD, p(out)) == 1
-        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), SUB, p(out)) == 1
-        assert hostsim.hs_jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), NOP, p(out)) == 0 and pt_from96(out) == a
+    for jf_add, jf_dbl in ((hostsim.hs_jf_add, hostsim.hs_jf_dbl), (hostsim.hs_jf_add_fused, hostsim.hs_jf_dbl_fused)):
+        for i, a in enumerate(pts):
+            wa, wb = ws[i % len(ws)], ws[(3 * i + 1) % len(ws)]
+            b = pts[(i + 2) % len(pts)]
+            A, B = pt_to96(a), pt_to96(b)
+            assert jf_dbl(p(A), C.c_uint64(wa), p(out)) == 0 and pt_from96(out) == o.pt_add(a, a)
+            for mode, want in ((ADD, o.pt_add(a, b)), (SUB, o.pt_add(a, o.pt_neg(b))), (SET, b), (SETNEG, o.pt_neg(b)), (NOP, a)):
+                assert jf_add(p(A), C.c_uint64(wa), p(B), C.c_uint64(wb), mode, p(out)) == 0
+                assert pt_from96(out) == want, (i, mode)
+            # exceptional inputs are reported when active, ignored when masked
+            assert jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), ADD, p(out)) == 1
+            assert jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), SUB, p(out)) == 1
+            assert jf_add(p(A), C.c_uint64(wa), p(A), C.c_uint64(wb), NOP, p(out)) == 0 and pt_from96(out) == a
     t2 = o.pt_mul(kat, o.COFACTOR // 2 * o.Q)
     assert hostsim.hs_jf_dbl(p(pt_to96(t2)), C.c_uint64(5), p(out)) == 1
+    assert hostsim.hs_jf_dbl_fused(p(pt_to96(t2)), C.c_uint64(5), p(out)) == 1
 
 
 def test_executed_multiply_counts_match_design_doc(hostsim):
@@ -446,3 +448,14 @@ def test_windowed_tonelli_shanks_in_fp(hostsim):
             assert r.value < o.P and r.value * r.value % o.P == a
             n_sq += 1
     assert 100 < n_sq < len(vals) - 100
+
+
+def test_lazily_reduced_building_blocks_accept_non_canonical_operands(hostsim):
+    """fp6_mul_nc / fp6_sqr_sub2 / fp6_sqr_sub_scaled / fp6_mul_sub_scaled / fused cofactor (csrc/debug_ops.cuh) with
+    operands in [p, 2^64) wherever the fast path hands them non-canonical values."""
+    from util import check_lazy_ops, lazy_ops_inputs
+    a, b = lazy_ops_inputs(np.random.default_rng(61))
+    out = np.zeros((len(a), 8, 6), dtype=np.uint64)
+    for i in range(len(a)):
+        hostsim.hs_debug_lazy_ops(p(a[i].copy()), p(b[i].copy()), p(out[i]))
+    check_lazy_ops(a, b, out)

@@ -44,3 +44,14 @@ def test_field_ops_edge_and_random():
             assert got[6] == o.f6_inv(ta), i
         if i % 16 == 0:
             assert got[7] == tuple(pow(x, o.INV_ALPHA, o.P) for x in ta), i
+
+
+def test_lazily_reduced_building_blocks_on_device():
+    """The lazily reduced forms k_verify_fast is built from (fp6_mul_nc, fp6_sqr_sub2, fp6_sqr_sub_scaled,
+    fp6_mul_sub_scaled, the fused cofactor/norm, non-canonical scalings) on the device, with non-canonical operands
+    wherever the kernel may hand them one."""
+    import schnorr_sig_b200 as s
+    from util import check_lazy_ops, lazy_ops_inputs
+    eng = s.default_engine(0)
+    a, b = lazy_ops_inputs(np.random.default_rng(62), n_random=1500)
+    check_lazy_ops(a, b, eng.debug_lazy_ops(a, b))

@@ -64,3 +64,43 @@ def pt_to96(pt):
 
 
 KAT96 = pt_to96((o.KAT_X, o.KAT_Y))
+
+
+# ---- lazily reduced building blocks (csrc/debug_ops.cuh): expected values and input sets -----------------------
+def lazy_ops_inputs(rng, n_random=200):
+    """(a, b) pairs for debug_lazy_ops: a holds ARBITRARY 64-bit limbs (incl. non-canonical ones), b canonical limbs."""
+    P = o.P
+    nc_edge = [0, 1, P - 1, P, P + 1, 2**64 - 1, 2**64 - 2, 2**64 - 2**32, 2**64 - 2**32 + 1, P + 2**32 - 2, 2**63,
+               2**32 - 1, 2**32, 0xFFFFFFFF00000000, 0xFFFFFFFFFFFF0000]
+    c_edge = [0, 1, 2, P - 1, P - 2, 2**32 - 1, 2**32, P - 2**32, (P - 1) // 2, 2**63]
+    a, b = [], []
+    for i, x in enumerate(nc_edge):
+        for j, y in enumerate(c_edge):
+            a.append([(x if (k + i) % 3 else nc_edge[(i + k) % len(nc_edge)]) for k in range(6)])
+            b.append([(y if (k + j) % 2 else c_edge[(j + k) % len(c_edge)]) for k in range(6)])
+    a += [[2**64 - 1] * 6, [P] * 6, [0] * 6]
+    b += [[P - 1] * 6, [P - 1] * 6, [1, 0, 0, 0, 0, 0]]
+    for _ in range(n_random):
+        a.append([int(v) for v in rng.integers(0, 2**64, 6, dtype=np.uint64)])
+        b.append([int(v) for v in rand_fp(rng, 6)])
+    return np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64)
+
+
+def check_lazy_ops(a, b, out):
+    """out[i] = the 8 results of debug_lazy_ops for (a[i], b[i]); asserts them against the big-int oracle."""
+    P = o.P
+    for i in range(len(a)):
+        ta = tuple(int(v) % P for v in a[i])
+        tb = tuple(int(v) for v in b[i])
+        ar = ta[1:] + ta[:1]
+        br = tb[5:] + tb[:5]
+        got = [tuple(int(v) for v in out[i, j]) for j in range(8)]
+        assert got[0] == o.f6_mul(ta, ar), i
+        assert got[1] == o.f6_sub(o.f6_sub(o.f6_sqr(ta), tb), tb), i
+        assert got[2] == o.f6_sub(o.f6_sub(o.f6_sqr(ta), tb), o.f6_scalar(br, ta[3])), i
+        assert got[3] == o.f6_sub(o.f6_mul(ta, ar), o.f6_scalar(tb, ta[5])), i
+        n = got[5][0]
+        assert got[5][1:] == (0, 0, 0, 0, 0) and (n == 0) == (not any(tb)), i
+        assert o.f6_mul(tb, got[4]) == (n, 0, 0, 0, 0, 0), i
+        want = o.f6_sub(o.f6_scalar(tb, ta[0]), o.f6_scalar(br, ta[1]))
+        assert got[6] == want and got[7] == want, i
