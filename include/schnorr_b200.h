@@ -62,14 +62,17 @@ uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx *ctx);
 int schnorr_b200_last_kernel_ms(schnorr_b200_ctx *ctx, float *ms);
 /* Single verification runs a fast path (inversion-free affine formulas, denominators kept in Fp) and re-runs the items
  * that hit one of its exceptional cases (identity / small-order keys, colliding partial sums) through the exact Jacobian kernel.
- * exact_only = 1 sends everything through the exact kernel (A/B measurements, tests; also env SB_VERIFY_EXACT=1).
+ * exact_only = 1 sends everything through the exact kernel (A/B measurements, tests).
  * last_exact_count: how many items of the last verify_many* call took the exact kernel (synchronises). */
 int schnorr_b200_set_exact_only(schnorr_b200_ctx *ctx, int exact_only);
 int schnorr_b200_last_exact_count(schnorr_b200_ctx *ctx, uint64_t *count);
 /* Calls of at most `max_signatures` signatures (per pipeline chunk) run the warp-cooperative kernel (one signature per
  * six lanes: ~4x lower latency, 6x more parallelism per signature, ~1.5x the work); larger calls the one-signature-per-
- * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 10240 (measured crossover ~12 k); env SB_DIST_MAX overrides at creation. */
+ * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 10240 (measured crossover ~12 k). */
 int schnorr_b200_set_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
+/* Test hook: force the Pippenger window width (4..16, 0 = planner's choice) and the segment length of the bucket
+ * accumulation (>= 8, 0 = automatic) of the batch path, to exercise the skewed-bucket code paths. */
+int schnorr_b200_set_msm_geometry(schnorr_b200_ctx *ctx, int window_bits, unsigned segment_len);
 
 /* hash_message(&Fp6, &PublicKey, &[u8]) -> [u8; 32]            src/signature.rs:274-306
  * rx48: n x 48 B (R.x limbs), pk96: n x 96 B, digests: n x 32 B.  */

@@ -21,6 +21,7 @@ _SIGNATURES = {
     "schnorr_b200_set_exact_only": (C.c_int, [C.c_void_p, C.c_int]),
     "schnorr_b200_last_exact_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "schnorr_b200_set_dist_threshold": (C.c_int, [C.c_void_p, _sz]),
+    "schnorr_b200_set_msm_geometry": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
     "schnorr_b200_hash_messages": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 5),
     "schnorr_b200_hash_messages_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 5),
     "schnorr_b200_verify_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6),
@@ -53,7 +54,7 @@ def lib():
     """Loads (building first if stale) schnorr-sig_b200/csrc/libschnorr_b200.so."""
     global _LIB
     if _LIB is None:
-        so = os.environ.get("SCHNORR_B200_LIB") or _build.build()   # override = kernel-variant experiments only
+        so = _build.build()
         if not os.path.exists(so):
             raise RuntimeError("libschnorr_b200.so is missing and could not be built; there is no CPU fallback")
         L = C.CDLL(so)

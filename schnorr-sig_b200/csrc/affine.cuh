@@ -176,7 +176,24 @@ template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     fp6 X = p->X, Y = p->Y, c;
     fp_t w = p->w, n;
-    fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / m,  m = 2 n
+    fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / (2 n)
+    if (FUSED) {
+        // slope = (3 X^2 + w^4) c / (2 n w) = (X^2 + w^4 / 3) c / (m w) with m = 2 n / 3: the factor 3 moves into the
+        // denominator (one product by a constant) instead of tripling the six coefficients of X^2
+        const fp_t inv3 = 0xaaaaaaaa00000001ULL, two_thirds = 0x5555555500000001ULL;
+        fp_t m = fp_mul(n, two_thirds);
+        fp_t w4 = fp_mul(fp_sqr_nc(fp_sqr_nc(w)), inv3);
+        fp6 num = fp6_sqr_nc(X);
+        num.c[0] = fp_add(num.c[0], w4);    // (a non-canonical minuend is fine, fp_sub)
+        fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
+        fp6 A = fp6_scale(X, m2);
+        fp6 L = fp6_mul_nc(num, c);         // slope = L / (m w)
+        fp6 X3 = fp6_sqr_sub2(L, A);
+        p->Y = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
+        p->X = X3;
+        p->w = fp_mul(m, w);
+        return n == 0;
+    }
     fp_t m = fp_add(n, n);
     fp_t w4 = fp_sqr(fp_sqr_nc(w));
     fp6 xx = fp6_sqr(X);
@@ -184,16 +201,9 @@ SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
     num.c[0] = fp_add(num.c[0], w4);        // 3 X^2 + a w^4, a = 1
     fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
     fp6 A = fp6_scale(X, m2);
-    fp6 X3, Y3;
-    if (FUSED) {
-        fp6 L = fp6_mul_nc(num, c);         // slope = L / (m w)
-        X3 = fp6_sqr_sub2(L, A);
-        Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
-    } else {
-        fp6 L = fp6_mul(num, c);
-        X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
-        Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
-    }
+    fp6 L = fp6_mul(num, c);
+    fp6 X3 = fp6_sub(fp6_sub(fp6_sqr(L), A), A);
+    fp6 Y3 = fp6_sub(fp6_mul(L, fp6_sub(A, X3)), fp6_scale(Y, m3));
     p->X = X3;
     p->Y = Y3;
     p->w = fp_mul(m, w);

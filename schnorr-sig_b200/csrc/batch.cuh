@@ -24,7 +24,7 @@ struct msm_plan {
     int chunk_sz; // buckets per chunk
 };
 
-static msm_plan msm_make_plan(size_t npoints) {
+static msm_plan msm_make_plan(size_t npoints, int c_override = 0) {
     double best = 1e300;
     msm_plan p{};
     for (int c = 4; c <= 16; c++) {
@@ -38,13 +38,10 @@ static msm_plan msm_make_plan(size_t npoints) {
             p.B = 1 << (c - 1);
         }
     }
-    if (const char* ov = getenv("SB_MSM_C")) {  // experiment knob: force the window width
-        int c = atoi(ov);
-        if (c >= 4 && c <= 16) {
-            p.c = c;
-            p.K = (256 + c - 1) / c;
-            p.B = 1 << (c - 1);
-        }
+    if (c_override >= 4 && c_override <= 16) {  // schnorr_b200_set_msm_geometry (tests): force the window width
+        p.c = c_override;
+        p.K = (256 + p.c - 1) / p.c;
+        p.B = 1 << (p.c - 1);
     }
     // bucket-reduction chunks: aim at ~8k chunk threads in total (short serial chains), 8..32 buckets each
     int want = (int)(((double)p.B * p.K) / 8192.0);
@@ -686,7 +683,11 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
         ctx->err = "batch too large for 31-bit point indices";
         return SCHNORR_B200_EARG;
     }
-    msm_plan pl = msm_make_plan(npts);
+    msm_plan pl = msm_make_plan(npts, ctx->msm_c_override);
+    if (npts * (size_t)pl.K >= 0xffffffffull) {  // sorted positions, offsets and counts are 32-bit
+        ctx->err = "batch too large for 32-bit bucket offsets: split it (n * windows must stay below 2^31)";
+        return SCHNORR_B200_EARG;
+    }
     size_t nslots = (size_t)pl.K * (pl.B + 1);
     void *d_pts, *d_sc, *d_lin, *d_cnt, *d_sorted, *d_buckets, *d_small;
     if (int rc = ensure_scratch(ctx, SL_D, npts * 96, &d_pts)) return rc;
@@ -702,7 +703,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     // 8 (small batches: more, shorter chains -- the accumulation is latency-bound there) .. 32 entries per thread
     uint32_t T = 32;
     while (T > 8 && max_entries / T < 65536) T /= 2;
-    if (const char* ov = getenv("SB_MSM_T")) T = (uint32_t)atoi(ov) >= 8 ? (uint32_t)atoi(ov) : 32;  // experiment knob
+    if (ctx->msm_t_override) T = ctx->msm_t_override;  // schnorr_b200_set_msm_geometry (tests)
     while ((max_entries + T - 1) / T > ((size_t)1 << 20)) T *= 2;
     size_t nseg = ((max_entries + T - 1) / T + 127) / 128 * 128;
     void* d_parts;
@@ -819,6 +820,7 @@ int schnorr_b200_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
         if (int rc = schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial))
             return rc;
     } else {
+        CHECK_MSG_OFF(ctx, n, msg_off);
         size_t mb = msg_off[n];
         if (mb && !msgs) return SCHNORR_B200_EARG;
         // staging slots distinct from those batch_partial_impl uses (A-G, J-L): reuse H/I plus the

@@ -74,7 +74,7 @@ SB_DEV void fp6_mul_body(fp6& r, const fp6& a, const fp6& b) {
 //   MODE 1:  a^2 - 2 A              (A canonical; p - A_k starts the accumulator and is doubled with the cross terms)
 //   MODE 2:  a^2 - A - B s          (A, B canonical; s any 64-bit representative of an Fp element)
 // These are X3 = L^2 - 2 X m^2 and X3 = L^2 - x1 w3^2 - x2 w3^2 of the point formulas in affine.cuh.
-template <int MODE>
+template <int MODE, bool CANON = true>
 SB_DEV void fp6_sqr_body_t(fp6& r, const fp6& a, const fp6* A, const fp6* B, fp_t s) {
     fp_t a7[6];
 #pragma unroll
@@ -102,7 +102,7 @@ SB_DEV void fp6_sqr_body_t(fp6& r, const fp6& a, const fp6* A, const fp6* B, fp_
             wide_add64(w, FP_P - A->c[k]);
             wide_mac(w, FP_P - B->c[k], s);
         }
-        r.c[k] = wide_reduce(w);
+        r.c[k] = wide_reduce_t<CANON>(w);
     }
 }
 SB_DEV void fp6_sqr_body(fp6& r, const fp6& a) { fp6_sqr_body_t<0>(r, a, nullptr, nullptr, 0); }
@@ -165,6 +165,12 @@ SB_DEV_NOINLINE fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
 SB_DEV_NOINLINE fp6 fp6_mul_nc(fp6 a, fp6 b) {
     fp6 r;
     fp6_mul_body<false>(r, a, b);
+    return r;
+}
+// a^2 with non-canonical coefficients
+SB_DEV_NOINLINE fp6 fp6_sqr_nc(fp6 a) {
+    fp6 r;
+    fp6_sqr_body_t<0, false>(r, a, nullptr, nullptr, 0);
     return r;
 }
 // a^2 - 2 A

@@ -44,7 +44,9 @@ struct schnorr_b200_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
-    bool exact_only = false;                        // SB_VERIFY_EXACT=1: skip the fast path (A/B measurements, tests)
+    bool exact_only = false;                        // schnorr_b200_set_exact_only: skip the fast path (A/B measurements, tests)
+    int msm_c_override = 0;                         // schnorr_b200_set_msm_geometry (tests): forced window width / segment length
+    uint32_t msm_t_override = 0;
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
@@ -624,6 +626,22 @@ static int alloc_soa(schnorr_b200_ctx* ctx, size_t n, soa_batch* b) {
     return 0;
 }
 
+// The offset table of a HOST call must start at 0 and be non-decreasing (the reference's `&[&[u8]]` cannot express
+// anything else); a bad table would otherwise turn into out-of-bounds device reads.  O(n) on the host.
+static bool msg_off_valid(size_t n, const uint64_t* msg_off) {
+    if (msg_off[0] != 0) return false;
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return false;
+    return true;
+}
+#define CHECK_MSG_OFF(ctx, n, msg_off)                                                            \
+    do {                                                                                          \
+        if (!msg_off_valid((n), (msg_off))) {                                                     \
+            (ctx)->err = "message offsets must start at 0 and be non-decreasing";                 \
+            return SCHNORR_B200_EARG;                                                             \
+        }                                                                                         \
+    } while (0)
+
 // host -> device staging helper
 static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t bytes, void** dev) {
     if (int rc = ensure_scratch(ctx, slot, bytes, dev)) return rc;
@@ -691,12 +709,6 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     cudaDeviceProp prop;
     CREATE_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
-    {
-        const char* ex = getenv("SB_VERIFY_EXACT");
-        ctx->exact_only = ex && ex[0] == '1';
-        const char* dm = getenv("SB_DIST_MAX");
-        if (dm) ctx->dist_max = (size_t)strtoull(dm, nullptr, 10);
-    }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     {
@@ -775,6 +787,13 @@ int schnorr_b200_set_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures
     ctx->dist_max = max_signatures;
     return SCHNORR_B200_OK;
 }
+int schnorr_b200_set_msm_geometry(schnorr_b200_ctx* ctx, int window_bits, unsigned segment_len) {
+    if (!ctx || (window_bits != 0 && (window_bits < 4 || window_bits > 16)) || (segment_len != 0 && segment_len < 8))
+        return SCHNORR_B200_EARG;
+    ctx->msm_c_override = window_bits;
+    ctx->msm_t_override = segment_len;
+    return SCHNORR_B200_OK;
+}
 int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {
     if (!ctx || !count) return SCHNORR_B200_EARG;
     *count = 0;
@@ -809,6 +828,7 @@ int schnorr_b200_hash_messages(schnorr_b200_ctx* ctx, size_t n, const uint8_t* r
     if (!ctx || (n && (!rx48 || !pk96 || !msg_off || !digests))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CHECK_MSG_OFF(ctx, n, msg_off);
     size_t mb = msg_off[n];
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_rx, *d_pk, *d_m, *d_off, *d_out;
@@ -851,6 +871,7 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
     if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CHECK_MSG_OFF(ctx, n, msg_off);
     size_t mb = msg_off[n];
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_out;
@@ -904,8 +925,11 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, ks)) return rc;
         cudaEventRecord(ctx->ev_k1, ks);
         ctx->launches += 1;
-        CUDA_TRY(ctx, cudaMemcpyAsync(verdicts + lo, (uint8_t*)d_out + lo, cn, cudaMemcpyDeviceToHost, ks));
     }
+    // verdicts come back after EVERY chunk has been enqueued: a device-to-host copy into pageable memory blocks the
+    // host until the kernels before it have finished, which would serialise the pipeline above (1 byte per signature:
+    // nothing to overlap anyway)
+    CUDA_TRY(ctx, cudaMemcpyAsync(verdicts, d_out, n, cudaMemcpyDeviceToHost, ks));
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaStreamSynchronize(ks));
     return SCHNORR_B200_OK;
@@ -937,6 +961,7 @@ int schnorr_b200_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_
     if (!ctx || (n && (!keyed130 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CHECK_MSG_OFF(ctx, n, msg_off);
     size_t mb = msg_off[n];
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_rec, *d_m, *d_off, *d_out;
@@ -970,6 +995,7 @@ int schnorr_b200_keygen(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, ui
     if (int rc = ensure_scratch(ctx, SL_E, n * 96, &d_pk)) return rc;
     if (int rc = ensure_scratch(ctx, SL_I, n, &d_inf)) return rc;
     if (int rc = schnorr_b200_keygen_dev(ctx, n, (uint8_t*)d_sk, (uint8_t*)d_pk, (uint8_t*)d_inf)) return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_sk, 0, n * 32, ctx->stream));  // the staging arena is reused: do not keep secret keys in it
     CUDA_TRY(ctx, cudaMemcpyAsync(pk96, d_pk, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
     if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(pk_inf, d_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -993,6 +1019,7 @@ int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32,
     if (!ctx || (n && (!sk32 || !pk96 || !msg_off || !nonce32 || !sigs81))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CHECK_MSG_OFF(ctx, n, msg_off);
     size_t mb = msg_off[n];
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_sk, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_nonce, *d_out;
@@ -1007,6 +1034,8 @@ int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32,
     if (int rc = schnorr_b200_sign_many_dev(ctx, n, (uint8_t*)d_sk, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
                                             (uint64_t*)d_off, (uint8_t*)d_nonce, (uint8_t*)d_out))
         return rc;
+    CUDA_TRY(ctx, cudaMemsetAsync(d_sk, 0, n * 32, ctx->stream));      // secret keys and nonces do not stay in the
+    CUDA_TRY(ctx, cudaMemsetAsync(d_nonce, 0, n * 32, ctx->stream));   // reusable staging arena
     CUDA_TRY(ctx, cudaMemcpyAsync(sigs81, d_out, n * 81, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SCHNORR_B200_OK;
