@@ -22,6 +22,13 @@
 #define SB_DEV_NOINLINE static __attribute__((noinline))
 #endif
 
+// SB_FOLD_WIDE = 1: the fold x2 * (2^32 - 1) of a reduction is ONE multiply-add (IMAD.WIDE with carry-out) and the
+// two wrap corrections (carry of the fold, borrow of the 2^96 term) are applied together -- 3 instructions less per
+// reduction than the add/subtract form (the kernels are bound by instruction count, profiles/r2_variants.md).
+#ifndef SB_FOLD_WIDE
+#define SB_FOLD_WIDE 1
+#endif
+
 namespace sb {
 
 // TEST-ONLY (tests/hostsim): count the 32x32->64 multiplies an algorithm executes, for the cost figures in DESIGN.md
@@ -70,6 +77,19 @@ SB_DEV fp_t fp_dbl(fp_t a) { return fp_add(a, a); }
 SB_DEV fp_t fp_reduce96_nc(uint32_t x0, uint32_t x1, uint32_t x2) {
 #if defined(__CUDA_ARCH__)
     uint32_t t0, t1;
+#if SB_FOLD_WIDE
+    asm("{\n\t"
+        ".reg .u32 c;\n\t"
+        "mad.lo.cc.u32 %0, %4, 0xffffffff, %2;\n\t"   // (x1:x0) + x2 * (2^32 - 1)
+        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"
+        "addc.u32 c, 0, 0;\n\t"                       // wrapped 2^64 == EPS
+        "sub.u32 c, 0, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(t0), "=&r"(t1)
+        : "r"(x0), "r"(x1), "r"(x2));
+#else
     asm("{\n\t"
         ".reg .u32 m0, m1, c;\n\t"
         "sub.cc.u32 m0, 0, %4;\n\t"       // (m1:m0) = x2 * (2^32 - 1)
@@ -83,6 +103,7 @@ SB_DEV fp_t fp_reduce96_nc(uint32_t x0, uint32_t x1, uint32_t x2) {
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(x0), "r"(x1), "r"(x2));
+#endif
     return ((uint64_t)t1 << 32) | t0;
 #else
     uint64_t t = ((uint64_t)x1 << 32) | x0;
@@ -93,8 +114,8 @@ SB_DEV fp_t fp_reduce96_nc(uint32_t x0, uint32_t x1, uint32_t x2) {
 #endif
 }
 // ... -> canonical x mod p
-SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
-    fp_t r = fp_reduce96_nc(x0, x1, x2);
+// any 64-bit representative -> the canonical one (select form: no 64-bit compare / subtract)
+SB_DEV fp_t fp_canon_sel(fp_t r) {
 #if defined(__CUDA_ARCH__)
     uint32_t t0 = (uint32_t)r, t1 = (uint32_t)(r >> 32);
     bool ge = (t1 == 0xffffffffu) & (t0 != 0);  // t >= p  <=>  high word all ones and low word >= 1
@@ -106,6 +127,7 @@ SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
     return r;
 #endif
 }
+SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) { return fp_canon_sel(fp_reduce96_nc(x0, x1, x2)); }
 
 // x = x0 + x1*2^32 + x2*2^64 + x3*2^96 + x4*2^128  ->  x mod p
 // using 2^64 = 2^32-1, 2^96 = -1, 2^128 = -2^32 (mod p):
@@ -113,7 +135,30 @@ SB_DEV fp_t fp_reduce96(uint32_t x0, uint32_t x1, uint32_t x2) {
 // x4 must be small (< 2^31): it only ever holds the carries of a dot product.
 template <bool CANON>
 SB_DEV fp_t fp_reduce160_t(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && SB_FOLD_WIDE
+    // V = (x1:x0) + x2 (2^32 - 1) - (x4:x3) lies in (-2^40, 2^65 - 2^33): the fold may carry (c = 1), the subtraction
+    // may borrow (m = -1); the net multiple k = c + m of 2^64 = EPS (mod p) is applied once -- (t + k EPS) cannot wrap
+    // again (k = 1: t <= 2^64 - 2^33; k = -1: t >= 2^64 - 2^40).
+    uint32_t t0, t1;
+    asm("{\n\t"
+        ".reg .u32 c, m, k;\n\t"
+        "mad.lo.cc.u32 %0, %4, 0xffffffff, %2;\n\t"
+        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %5;\n\t"
+        "subc.cc.u32 %1, %1, %6;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "add.u32 k, c, m;\n\t"
+        "sub.u32 m, 0, k;\n\t"            // k EPS = (k >> 31 : -k) in two's complement
+        "shr.s32 c, k, 31;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, c;\n\t"
+        "}"
+        : "=&r"(t0), "=&r"(t1)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4));
+    fp_t r = ((uint64_t)t1 << 32) | t0;
+    return CANON ? fp_canon_sel(r) : r;
+#elif defined(__CUDA_ARCH__)
     uint32_t t0, t1;
     asm("{\n\t"
         ".reg .u32 m;\n\t"
@@ -286,6 +331,19 @@ SB_DEV fp_t fp_mul_nc(fp_t a, fp_t b) {
         "mad.lo.cc.u32 p1, %3, %4, p1;\n\t"
         "madc.hi.cc.u32 p2, %3, %4, p2;\n\t"
         "addc.u32 p3, p3, 0;\n\t"
+#if SB_FOLD_WIDE
+        "mad.lo.cc.u32 %0, p2, 0xffffffff, p0;\n\t"   // (p1:p0) + p2 * (2^32 - 1)   [2^64 == 2^32 - 1]
+        "madc.hi.cc.u32 %1, p2, 0xffffffff, p1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, p3;\n\t"                  // - p3                        [2^96 == -1]
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "add.u32 m0, c, m;\n\t"                       // net multiple of 2^64 == EPS: -1, 0, 1 (fp_reduce160_t)
+        "sub.u32 m, 0, m0;\n\t"
+        "shr.s32 c, m0, 31;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, c;\n\t"
+#else
         "sub.cc.u32 %0, p0, p3;\n\t"      // (p1:p0) - p3          [2^96 == -1]
         "subc.cc.u32 %1, p1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
@@ -299,6 +357,7 @@ SB_DEV fp_t fp_mul_nc(fp_t a, fp_t b) {
         "sub.u32 c, 0, c;\n\t"
         "add.cc.u32 %0, %0, c;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
+#endif
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
@@ -325,6 +384,19 @@ SB_DEV fp_t fp_sqr_nc(fp_t a) {
         "add.cc.u32 p1, p1, c0;\n\t"
         "addc.cc.u32 p2, p2, c1;\n\t"
         "addc.u32 p3, p3, c2;\n\t"
+#if SB_FOLD_WIDE
+        "mad.lo.cc.u32 %0, p2, 0xffffffff, p0;\n\t"
+        "madc.hi.cc.u32 %1, p2, 0xffffffff, p1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, p3;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "add.u32 m0, c, m;\n\t"
+        "sub.u32 m, 0, m0;\n\t"
+        "shr.s32 c, m0, 31;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, c;\n\t"
+#else
         "sub.cc.u32 %0, p0, p3;\n\t"
         "subc.cc.u32 %1, p1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
@@ -338,6 +410,7 @@ SB_DEV fp_t fp_sqr_nc(fp_t a) {
         "sub.u32 c, 0, c;\n\t"
         "add.cc.u32 %0, %0, c;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
+#endif
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(a0), "r"(a1));
@@ -370,6 +443,14 @@ SB_DEV fp_t fp_mul7_nc(fp_t a) {
         "mul.hi.u32 x1, %2, 7;\n\t"
         "mad.lo.cc.u32 %1, %3, 7, x1;\n\t"
         "madc.hi.u32 x2, %3, 7, 0;\n\t"
+#if SB_FOLD_WIDE
+        "mad.lo.cc.u32 %0, x2, 0xffffffff, %0;\n\t"   // + x2 * (2^32 - 1)
+        "madc.hi.cc.u32 %1, x2, 0xffffffff, %1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "sub.u32 c, 0, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+#else
         "sub.cc.u32 m0, 0, x2;\n\t"       // + x2 * (2^32 - 1)
         "subc.u32 m1, x2, 0;\n\t"
         "add.cc.u32 %0, %0, m0;\n\t"
@@ -378,6 +459,7 @@ SB_DEV fp_t fp_mul7_nc(fp_t a) {
         "sub.u32 c, 0, c;\n\t"
         "add.cc.u32 %0, %0, c;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
+#endif
         "}"
         : "=&r"(t0), "=&r"(t1)
         : "r"(a0), "r"(a1));
