@@ -50,6 +50,17 @@ typedef struct schnorr_b200_ctx schnorr_b200_ctx;
 /* Creates a context on CUDA device `device`: stream, scratch arena and the fixed-base table of G
  * (the reference's `cheetah::BASEPOINT_TABLE`, src/signature.rs:19) built on the device. */
 int schnorr_b200_create(int device, schnorr_b200_ctx **out);
+/* Multi-device context: one stream, scratch arena and fixed-base table per listed CUDA device.
+ * The HOST entry points (verify_many, verify_keyed_many, hash_messages, verify_batch, keygen, sign_many) then shard
+ * every call over the devices in contiguous slices -- independent verification without any exchange, batch
+ * verification with ONE 192-byte peer copy per device (partial MSM point + partial scalar) to the first device, where
+ * the batch is finished.  This is what `verify_batch(&[Signature], &[PublicKey], &[&[u8]], rng)` (src/batch.rs:31-36)
+ * and a loop over `Signature::verify` bind to on an 8-GPU box.  The *_dev entry points and set_stream need a
+ * single-device context (device buffers live on one GPU) and return SCHNORR_B200_EARG here.  A device may be listed
+ * more than once (independent contexts on the same GPU).  n_devices == 1 is schnorr_b200_create. */
+int schnorr_b200_create_multi(const int *devices, int n_devices, schnorr_b200_ctx **out);
+/* number of device contexts behind `ctx` (1 for schnorr_b200_create) */
+int schnorr_b200_device_count(const schnorr_b200_ctx *ctx);
 void schnorr_b200_destroy(schnorr_b200_ctx *ctx);
 const char *schnorr_b200_last_error(const schnorr_b200_ctx *ctx);
 /* Use an external stream (e.g. the caller's current stream) for all subsequent work. NULL = own stream. */

@@ -763,6 +763,7 @@ int schnorr_b200_batch_partial_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_
                                    const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
                                    const uint8_t* rand32, uint8_t* partial192) {
     if (!ctx || !partial192 || (n && (!sigs81 || !pk96 || !msg_off || !rand32))) return SCHNORR_B200_EARG;
+    NOT_ON_MULTI(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (n == 0) {  // empty slice: identity point, zero scalar
         uint64_t h[24] = {0};
@@ -778,6 +779,7 @@ int schnorr_b200_batch_partial_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_
 int schnorr_b200_batch_finish_dev(schnorr_b200_ctx* ctx, size_t n_partials, const uint8_t* partials192,
                                   uint8_t* result216) {
     if (!ctx || !partials192 || !result216 || n_partials == 0) return SCHNORR_B200_EARG;
+    NOT_ON_MULTI(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     k_batch_finish<<<1, 32, 0, ctx->stream>>>(n_partials, (const uint64_t*)partials192, ctx->gtab, result216);
     ctx->launches += 1;
@@ -798,6 +800,7 @@ static int read_result(schnorr_b200_ctx* ctx, const uint8_t* d_res, int* verdict
 int schnorr_b200_batch_finish(schnorr_b200_ctx* ctx, size_t n_partials, const uint8_t* partials192_host, int* verdict,
                               uint8_t* lhs97, uint8_t* rhs97) {
     if (!ctx || !partials192_host || !verdict || n_partials == 0) return SCHNORR_B200_EARG;
+    MULTI_DISPATCH(ctx, schnorr_b200_batch_finish(ctx->shards[0], n_partials, partials192_host, verdict, lhs97, rhs97));
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     void *d_p, *d_res;
     if (int rc = stage_in(ctx, SL_H, partials192_host, n_partials * 192, &d_p)) return rc;
@@ -807,48 +810,54 @@ int schnorr_b200_batch_finish(schnorr_b200_ctx* ctx, size_t n_partials, const ui
     return read_result(ctx, res, verdict, lhs97, rhs97);
 }
 
+// host inputs -> staged on the device -> one 192-byte partial at `partial` (device memory of this context)
+static int batch_partial_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
+                              uint8_t* partial) {
+    if (n == 0) return schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial);
+    CHECK_MSG_OFF(ctx, n, msg_off);
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    // staging slots distinct from those batch_partial_impl uses (A-G, J-L): one blob in slot H
+    void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_rand;
+    size_t sz_sig = (n * 81 + 255) & ~(size_t)255, sz_pk = (n * 96 + 255) & ~(size_t)255,
+           sz_m = (mb + 255) & ~(size_t)255, sz_off = ((n + 1) * 8 + 255) & ~(size_t)255,
+           sz_rand = (n * 32 + 255) & ~(size_t)255, sz_inf = (n + 255) & ~(size_t)255;
+    void* blob;
+    if (int rc = ensure_scratch(ctx, SL_H, sz_sig + sz_pk + sz_m + sz_off + sz_rand + sz_inf, &blob)) return rc;
+    uint8_t* p = (uint8_t*)blob;
+    d_sig = p; p += sz_sig;
+    d_pk = p; p += sz_pk;
+    d_m = p; p += sz_m;
+    d_off = p; p += sz_off;
+    d_rand = p; p += sz_rand;
+    if (pk_inf) d_inf = p;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_sig, sigs81, n * 81, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_pk, pk96, n * 96, cudaMemcpyHostToDevice, st));
+    if (mb) CUDA_TRY(ctx, cudaMemcpyAsync(d_m, msgs, mb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_rand, rand32, n * 32, cudaMemcpyHostToDevice, st));
+    if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(d_inf, pk_inf, n, cudaMemcpyHostToDevice, st));
+    return batch_partial_impl(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m, (uint64_t*)d_off,
+                              (uint8_t*)d_rand, partial);
+}
+
+static int multi_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
+                              int* verdict, uint8_t* lhs97, uint8_t* rhs97);
+
 int schnorr_b200_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                               const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
                               int* verdict, uint8_t* lhs97, uint8_t* rhs97) {
     if (!ctx || !verdict || (n && (!sigs81 || !pk96 || !msg_off || !rand32))) return SCHNORR_B200_EARG;
+    if (!ctx->shards.empty()) return multi_verify_batch(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, verdict, lhs97, rhs97);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     void* d_res;
     if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192, &d_res)) return rc;
     uint8_t* res = (uint8_t*)d_res + 64;
     uint8_t* partial = res + RESULT_BYTES;
-    if (n == 0) {
-        if (int rc = schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial))
-            return rc;
-    } else {
-        CHECK_MSG_OFF(ctx, n, msg_off);
-        size_t mb = msg_off[n];
-        if (mb && !msgs) return SCHNORR_B200_EARG;
-        // staging slots distinct from those batch_partial_impl uses (A-G, J-L): reuse H/I plus the
-        // tail of dedicated buffers allocated here
-        void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_rand;
-        size_t sz_sig = (n * 81 + 255) & ~(size_t)255, sz_pk = (n * 96 + 255) & ~(size_t)255,
-               sz_m = (mb + 255) & ~(size_t)255, sz_off = ((n + 1) * 8 + 255) & ~(size_t)255,
-               sz_rand = (n * 32 + 255) & ~(size_t)255, sz_inf = (n + 255) & ~(size_t)255;
-        void* blob;
-        if (int rc = ensure_scratch(ctx, SL_H, sz_sig + sz_pk + sz_m + sz_off + sz_rand + sz_inf, &blob)) return rc;
-        uint8_t* p = (uint8_t*)blob;
-        d_sig = p; p += sz_sig;
-        d_pk = p; p += sz_pk;
-        d_m = p; p += sz_m;
-        d_off = p; p += sz_off;
-        d_rand = p; p += sz_rand;
-        if (pk_inf) d_inf = p;
-        cudaStream_t st = ctx->stream;
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_sig, sigs81, n * 81, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_pk, pk96, n * 96, cudaMemcpyHostToDevice, st));
-        if (mb) CUDA_TRY(ctx, cudaMemcpyAsync(d_m, msgs, mb, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_rand, rand32, n * 32, cudaMemcpyHostToDevice, st));
-        if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(d_inf, pk_inf, n, cudaMemcpyHostToDevice, st));
-        if (int rc = batch_partial_impl(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m,
-                                        (uint64_t*)d_off, (uint8_t*)d_rand, partial))
-            return rc;
-    }
+    if (int rc = batch_partial_host(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, partial)) return rc;
     if (int rc = schnorr_b200_batch_finish_dev(ctx, 1, partial, res)) return rc;
     return read_result(ctx, res, verdict, lhs97, rhs97);
 }

@@ -52,6 +52,8 @@ struct schnorr_b200_ctx {
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
     std::string err;
+    // multi-device context (schnorr_b200_create_multi): one single-device context per listed device; empty otherwise
+    std::vector<schnorr_b200_ctx*> shards;
 };
 
 #define CUDA_TRY(ctx, expr)                                                                      \
@@ -649,7 +651,21 @@ static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t by
     return 0;
 }
 
+#define MULTI_DISPATCH(ctx, call)                                  \
+    do {                                                           \
+        if ((ctx) && !(ctx)->shards.empty()) return call;          \
+    } while (0)
+#define NOT_ON_MULTI(ctx)                                                                                          \
+    do {                                                                                                           \
+        if ((ctx) && !(ctx)->shards.empty()) {                                                                     \
+            (ctx)->err = "device-pointer entry points need a single-device context (buffers live on one device)"; \
+            return SCHNORR_B200_EARG;                                                                              \
+        }                                                                                                          \
+    } while (0)
+
 #include "batch.cuh"
+#include "multi.cuh"
+
 
 // Signature::verify over an ingested SoA batch: fast path (per-thread or warp-cooperative by call size), then the exact kernel over the handful of
 // items it handed back.  `list_base` = first element of this batch in the per-call work list (pipelined chunks
@@ -741,8 +757,36 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     return SCHNORR_B200_OK;
 }
 
+int schnorr_b200_create_multi(const int* devices, int n_devices, schnorr_b200_ctx** out) {
+    if (!out) return SCHNORR_B200_EARG;
+    *out = nullptr;
+    if (!devices || n_devices <= 0 || n_devices > 64) return SCHNORR_B200_EARG;
+    if (n_devices == 1) return schnorr_b200_create(devices[0], out);
+    schnorr_b200_ctx* ctx = new schnorr_b200_ctx();
+    ctx->device = devices[0];
+    for (int k = 0; k < n_devices; k++) {
+        schnorr_b200_ctx* sh = nullptr;
+        int rc = schnorr_b200_create(devices[k], &sh);
+        if (rc != SCHNORR_B200_OK) {
+            schnorr_b200_destroy(ctx);
+            return rc;
+        }
+        ctx->shards.push_back(sh);
+    }
+    ctx->sm_count = ctx->shards[0]->sm_count;
+    ctx->verify_wave = ctx->shards[0]->verify_wave;
+    *out = ctx;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_device_count(const schnorr_b200_ctx* ctx) { return !ctx ? 0 : (ctx->shards.empty() ? 1 : (int)ctx->shards.size()); }
+
 void schnorr_b200_destroy(schnorr_b200_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->shards.empty()) {
+        for (schnorr_b200_ctx* sh : ctx->shards) schnorr_b200_destroy(sh);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     for (int s = 0; s < SL_COUNT; s++)
@@ -761,17 +805,35 @@ const char* schnorr_b200_last_error(const schnorr_b200_ctx* ctx) { return ctx ? 
 
 int schnorr_b200_set_stream(schnorr_b200_ctx* ctx, void* stream) {
     if (!ctx) return SCHNORR_B200_EARG;
+    NOT_ON_MULTI(ctx);
     ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_synchronize(schnorr_b200_ctx* ctx) {
     if (!ctx) return SCHNORR_B200_EARG;
+    for (schnorr_b200_ctx* sh : ctx->shards)
+        if (int rc = schnorr_b200_synchronize(sh)) return rc;
+    if (!ctx->shards.empty()) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SCHNORR_B200_OK;
 }
-uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t schnorr_b200_launch_count(const schnorr_b200_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t total = ctx->launches;
+    for (const schnorr_b200_ctx* sh : ctx->shards) total += sh->launches;
+    return total;
+}
 int schnorr_b200_last_kernel_ms(schnorr_b200_ctx* ctx, float* ms) {
     if (!ctx || !ms) return SCHNORR_B200_EARG;
+    if (!ctx->shards.empty()) {  // the slowest device
+        *ms = 0;
+        for (schnorr_b200_ctx* sh : ctx->shards) {
+            float m = 0;
+            if (int rc = schnorr_b200_last_kernel_ms(sh, &m)) return rc;
+            if (m > *ms) *ms = m;
+        }
+        return SCHNORR_B200_OK;
+    }
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_k1));
     CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
     return SCHNORR_B200_OK;
@@ -779,11 +841,13 @@ int schnorr_b200_last_kernel_ms(schnorr_b200_ctx* ctx, float* ms) {
 
 int schnorr_b200_set_exact_only(schnorr_b200_ctx* ctx, int exact_only) {
     if (!ctx) return SCHNORR_B200_EARG;
+    for (schnorr_b200_ctx* sh : ctx->shards) sh->exact_only = exact_only != 0;
     ctx->exact_only = exact_only != 0;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_set_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {
     if (!ctx) return SCHNORR_B200_EARG;
+    for (schnorr_b200_ctx* sh : ctx->shards) sh->dist_max = max_signatures;
     ctx->dist_max = max_signatures;
     return SCHNORR_B200_OK;
 }
@@ -792,11 +856,23 @@ int schnorr_b200_set_msm_geometry(schnorr_b200_ctx* ctx, int window_bits, unsign
         return SCHNORR_B200_EARG;
     ctx->msm_c_override = window_bits;
     ctx->msm_t_override = segment_len;
+    for (schnorr_b200_ctx* sh : ctx->shards) {
+        sh->msm_c_override = window_bits;
+        sh->msm_t_override = segment_len;
+    }
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {
     if (!ctx || !count) return SCHNORR_B200_EARG;
     *count = 0;
+    if (!ctx->shards.empty()) {
+        for (schnorr_b200_ctx* sh : ctx->shards) {
+            uint64_t c = 0;
+            if (int rc = schnorr_b200_last_exact_count(sh, &c)) return rc;
+            *count += c;
+        }
+        return SCHNORR_B200_OK;
+    }
     if (ctx->exact_counters_used == 0 || !ctx->scratch[SL_M]) return SCHNORR_B200_OK;
     uint32_t c[schnorr_b200_ctx::MAX_CHUNKS] = {};
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -809,6 +885,7 @@ int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {
 // ---- hash_messages ---------------------------------------------------------------------------
 int schnorr_b200_hash_messages_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* rx48, const uint8_t* pk96,
                                    const uint8_t* msgs, const uint64_t* msg_off, uint8_t* digests) {
+    NOT_ON_MULTI(ctx);
     if (!ctx || (n && (!rx48 || !pk96 || !msg_off || !digests))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -825,6 +902,7 @@ int schnorr_b200_hash_messages_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_
 
 int schnorr_b200_hash_messages(schnorr_b200_ctx* ctx, size_t n, const uint8_t* rx48, const uint8_t* pk96,
                                const uint8_t* msgs, const uint64_t* msg_off, uint8_t* digests) {
+    MULTI_DISPATCH(ctx, multi_hash_messages(ctx, n, rx48, pk96, msgs, msg_off, digests));
     if (!ctx || (n && (!rx48 || !pk96 || !msg_off || !digests))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -849,6 +927,7 @@ int schnorr_b200_hash_messages(schnorr_b200_ctx* ctx, size_t n, const uint8_t* r
 int schnorr_b200_verify_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                                  const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
                                  uint8_t* verdicts) {
+    NOT_ON_MULTI(ctx);
     if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -868,6 +947,7 @@ int schnorr_b200_verify_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t*
 // back as soon as its kernel ends, so the PCIe time hides behind the kernels.
 int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                              const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
+    MULTI_DISPATCH(ctx, multi_verify_many(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, verdicts));
     if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -938,6 +1018,7 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
 // ---- KeyedSignature::verify over wire records -------------------------------------------------
 int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,
                                        const uint64_t* msg_off, uint8_t* verdicts) {
+    NOT_ON_MULTI(ctx);
     if (!ctx || (n && (!keyed130 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -958,6 +1039,7 @@ int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx* ctx, size_t n, const ui
 }
 int schnorr_b200_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,
                                    const uint64_t* msg_off, uint8_t* verdicts) {
+    MULTI_DISPATCH(ctx, multi_verify_keyed_many(ctx, n, keyed130, msgs, msg_off, verdicts));
     if (!ctx || (n && (!keyed130 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -978,6 +1060,7 @@ int schnorr_b200_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_
 
 // ---- keygen / sign ---------------------------------------------------------------------------
 int schnorr_b200_keygen_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, uint8_t* pk96, uint8_t* pk_inf) {
+    NOT_ON_MULTI(ctx);
     if (!ctx || (n && (!sk32 || !pk96))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -987,6 +1070,7 @@ int schnorr_b200_keygen_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_keygen(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, uint8_t* pk96, uint8_t* pk_inf) {
+    MULTI_DISPATCH(ctx, multi_keygen(ctx, n, sk32, pk96, pk_inf));
     if (!ctx || (n && (!sk32 || !pk96))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1004,6 +1088,7 @@ int schnorr_b200_keygen(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, ui
 int schnorr_b200_sign_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, const uint8_t* pk96,
                                const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
                                const uint8_t* nonce32, uint8_t* sigs81) {
+    NOT_ON_MULTI(ctx);
     if (!ctx || (n && (!sk32 || !pk96 || !msg_off || !nonce32 || !sigs81))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1016,6 +1101,7 @@ int schnorr_b200_sign_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* s
 int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32, const uint8_t* pk96,
                            const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* nonce32,
                            uint8_t* sigs81) {
+    MULTI_DISPATCH(ctx, multi_sign_many(ctx, n, sk32, pk96, pk_inf, msgs, msg_off, nonce32, sigs81));
     if (!ctx || (n && (!sk32 || !pk96 || !msg_off || !nonce32 || !sigs81))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1044,6 +1130,7 @@ int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32,
 // ---- codecs ----------------------------------------------------------------------------------
 int schnorr_b200_decompress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* in49, uint8_t* pk96, uint8_t* pk_inf,
                             uint8_t* ok) {
+    MULTI_DISPATCH(ctx, schnorr_b200_decompress(ctx->shards[0], n, in49, pk96, pk_inf, ok));
     if (!ctx || (n && (!in49 || !pk96 || !pk_inf || !ok))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1063,6 +1150,7 @@ int schnorr_b200_decompress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* in49
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_compress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* pk96, const uint8_t* pk_inf, uint8_t* out49) {
+    MULTI_DISPATCH(ctx, schnorr_b200_compress(ctx->shards[0], n, pk96, pk_inf, out49));
     if (!ctx || (n && (!pk96 || !out49))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1081,6 +1169,7 @@ int schnorr_b200_compress(schnorr_b200_ctx* ctx, size_t n, const uint8_t* pk96, 
 
 // ---- test hook -------------------------------------------------------------------------------
 int schnorr_b200_debug_field_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t* a6, const uint64_t* b6, uint64_t* out48) {
+    MULTI_DISPATCH(ctx, schnorr_b200_debug_field_ops(ctx->shards[0], n, a6, b6, out48));
     if (!ctx || (n && (!a6 || !b6 || !out48))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1097,6 +1186,7 @@ int schnorr_b200_debug_field_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t
 }
 
 int schnorr_b200_debug_lazy_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t* a6, const uint64_t* b6, uint64_t* out48) {
+    MULTI_DISPATCH(ctx, schnorr_b200_debug_lazy_ops(ctx->shards[0], n, a6, b6, out48));
     if (!ctx || (n && (!a6 || !b6 || !out48))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1114,6 +1204,7 @@ int schnorr_b200_debug_lazy_ops(schnorr_b200_ctx* ctx, size_t n, const uint64_t*
 
 // ---- roofline calibration --------------------------------------------------------------------
 int schnorr_b200_imad_peak(schnorr_b200_ctx* ctx, int iters, double* wide_mul_per_s, double* elapsed_ms) {
+    MULTI_DISPATCH(ctx, schnorr_b200_imad_peak(ctx->shards[0], iters, wide_mul_per_s, elapsed_ms));
     if (!ctx || iters <= 0 || !wide_mul_per_s) return SCHNORR_B200_EARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     void* sink;

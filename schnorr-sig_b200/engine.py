@@ -1,4 +1,5 @@
-"""Array-level host API over the C ABI: one `Engine` = one `schnorr_b200_ctx` on one GPU.
+"""Array-level host API over the C ABI: one `Engine` = one `schnorr_b200_ctx` on one GPU, or -- given a list of
+devices -- one multi-device context (`schnorr_b200_create_multi`) whose host entry points shard every call.
 
 Buffers may be numpy arrays (host), torch tensors (host-pinned or CUDA) or raw integer addresses.
 The `*_dev` methods take device buffers, enqueue on the engine's stream and do not synchronise;
@@ -42,15 +43,26 @@ def _u8(a, cols=None):
 
 
 class Engine:
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: a CUDA device index, or a list of indices for a multi-device context (a device may repeat)."""
         self._L = _lib.lib()
         h = C.c_void_p()
-        rc = self._L.schnorr_b200_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._L.schnorr_b200_create_multi(devs, len(device), C.byref(h))
+            self.devices = [int(d) for d in device]
+        else:
+            rc = self._L.schnorr_b200_create(int(device), C.byref(h))
+            self.devices = [int(device)]
         if rc != 0 or not h.value:
-            raise EngineError("schnorr_b200_create(device=%d) failed with %d: a CUDA device is required "
+            raise EngineError("schnorr_b200_create(device=%r) failed with %d: a CUDA device is required "
                               "(there is no CPU fallback)" % (device, rc))
         self._h = h
-        self.device = int(device)
+        self.device = self.devices[0]
+
+    @property
+    def device_count(self) -> int:
+        return int(self._L.schnorr_b200_device_count(self._h))
 
     # ---- lifecycle -----------------------------------------------------------------------
     def close(self):
@@ -88,6 +100,10 @@ class Engine:
         """True: every verification goes through the exact Jacobian kernel (A/B measurements, tests)."""
         self._check(self._L.schnorr_b200_set_exact_only(self._h, 1 if flag else 0), "set_exact_only")
 
+    def set_msm_geometry(self, window_bits: int = 0, segment_len: int = 0):
+        """Test hook: force the Pippenger window width / segment length of the batch path (0 = automatic)."""
+        self._check(self._L.schnorr_b200_set_msm_geometry(self._h, int(window_bits), int(segment_len)), "set_msm_geometry")
+
     def set_dist_threshold(self, max_signatures: int):
         """Calls up to this many signatures use the six-lanes-per-signature kernel (0 = never, 2**62 = always)."""
         self._check(self._L.schnorr_b200_set_dist_threshold(self._h, int(max_signatures)), "set_dist_threshold")
@@ -110,6 +126,11 @@ class Engine:
         return out
 
     @staticmethod
+    def _check_inf(n, inf):
+        if inf is not None and inf.shape[0] != n:
+            raise AssertionError("pk_inf must hold one flag per public key")
+
+    @staticmethod
     def _check_offsets(n, npk, off, msgs):
         # the reference asserts equal lengths (src/batch.rs:37-44)
         if npk != n:
@@ -125,6 +146,7 @@ class Engine:
         n = sigs81.shape[0]
         self._check_offsets(n, pk96.shape[0], off, msgs)
         inf = None if pk_inf is None else _u8(pk_inf)
+        self._check_inf(n, inf)
         out = np.full(n, 255, dtype=np.uint8)
         self._check(self._L.schnorr_b200_verify_many(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(inf), _ptr(msgs),
                                                      _ptr(off), _ptr(out)), "verify_many")

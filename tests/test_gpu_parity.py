@@ -147,17 +147,23 @@ def test_affine_fast_path_agrees_with_exact_kernel_and_hands_back_exceptional_it
     f["pk"][5] = pt_to96(o.pt_mul(kat, order // 29))         # order 29: P + P / P - P inside the buckets
     f["inf"][7] = 1                                          # identity key
     want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
-    got_fast = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
-    handed_back = eng.last_exact_count()
-    eng.set_exact_only(True)
+    got, handed_back = {}, {}
     try:
-        got_exact = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        for name, thr in (("fast", 0), ("dist", 2**62)):      # one signature per thread / per six lanes
+            eng.set_dist_threshold(thr)
+            got[name] = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+            handed_back[name] = eng.last_exact_count()
+        eng.set_exact_only(True)
+        got["exact"] = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
         assert eng.last_exact_count() == 0
     finally:
         eng.set_exact_only(False)
-    assert np.array_equal(got_fast, want) and np.array_equal(got_exact, want)
-    assert 3 <= handed_back <= 3 + n // 100, handed_back       # the three adversarial keys + ~0.1 % of honest inputs
-    assert not (got_fast == 0xFF).any()
+        eng.set_dist_threshold(10240)
+    for name in ("fast", "dist", "exact"):
+        assert np.array_equal(got[name], want), name
+        assert not (got[name] == 0xFF).any()
+    for name in ("fast", "dist"):                              # the three adversarial keys + ~0.1 % of honest inputs
+        assert 3 <= handed_back[name] <= 3 + n // 100, (name, handed_back)
 
 
 @pytest.mark.parametrize("n", [1, 4, 5, 6, 21, 127, 1000])

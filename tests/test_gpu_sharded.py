@@ -117,7 +117,6 @@ def test_batch_with_skewed_randomisers_exercises_bucket_splitting():
 def test_batch_with_narrow_top_window_uses_the_block_fixup():
     """Window widths whose top window has only 3 bits (c = 6, 12, 14: a handful of buckets hold an eighth of all
     points each and span hundreds of segments -> k_msm_fixup_long) give the same points as the oracle."""
-    import os
     import schnorr_sig_b200 as s
     eng = s.default_engine(0)
     n = 6000
@@ -125,12 +124,12 @@ def test_batch_with_narrow_top_window_uses_the_block_fixup():
     cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"], cref.default_threads())
     assert cv == 0
     try:
-        for c in ("6", "12", "14", "9"):
-            os.environ["SB_MSM_C"] = c        # experiment knob of the host planner, read per call
+        for c, t in ((6, 0), (12, 0), (14, 8), (9, 64)):
+            eng.set_msm_geometry(c, t)        # test hook of the host planner (schnorr_b200_set_msm_geometry)
             v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"])
             assert v == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr), c
     finally:
-        os.environ.pop("SB_MSM_C", None)
+        eng.set_msm_geometry(0, 0)
 
 
 def test_mid_size_random_faults_against_oracle():
