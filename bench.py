@@ -35,37 +35,11 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
+import cost_model  # noqa: E402  (single source of the unit counts)
+from cost_model import permutations_for, w_per_hash, w_per_verify  # noqa: E402
+
 METRIC = "schnorr_verifications_per_sec"
 UNIT = "verifications/s"
-W_PER_VERIFY_L8 = 787338          # SURVEY.md §8(d) canonical cost model v1, 8-byte message
-W_PER_BATCH_SIG = 163900
-HBM_BYTES_PER_VERIFY = 177 + 8 + 8 + 1   # 81 sig + 96 key + msg + offset + verdict
-W_PER_PERMUTATION = 28140
-W_VERIFY_WITHOUT_HASH = W_PER_VERIFY_L8 - 2 * W_PER_PERMUTATION
-# multiplies the kernels actually EXECUTE per verification (counted by the test-only counter of the host build of the
-# device headers, tests/test_device_formulas_hostsim.py::test_executed_multiply_counts_match_design_doc)
-W_EXECUTED_FAST_L8 = 336813       # k_verify_fast: (X, Y, w) coordinates, 8-byte message (2 permutations)
-W_EXECUTED_PER_PERMUTATION = 28000
-
-
-def permutations_for(msg_len):
-    """Rescue permutations of hash_message: 13 fixed elements + ceil(L/7) message elements, rate 8;
-    a partial last block costs one more permutation (padding), a full one does not."""
-    elems = 13 + -(-msg_len // 7)
-    return -(-elems // 8)
-
-
-def w_per_verify(msg_len):
-    return W_VERIFY_WITHOUT_HASH + permutations_for(msg_len) * W_PER_PERMUTATION
-
-
-def w_per_hash(msg_len):
-    return permutations_for(msg_len) * W_PER_PERMUTATION
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_verify_fast launch from the ncu --set full capture
-# committed under profiles/ (per launch, keyed by log2 n); None where no capture exists
-TRAFFIC_BYTES_PER_LAUNCH = {20: 8.855e9, 17: 1.026e9}   # profiles/r1_k_verify_fast_ncu.txt (n = 2^20): 1.06 GB read + 7.80 GB written (thread-local buckets)
 
 
 def parse_args():
@@ -78,6 +52,8 @@ def parse_args():
     ap.add_argument("--msg-len", type=int, default=8)
     ap.add_argument("--no-extras", action="store_true", help="skip the hash / batch side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 2^log2n signatures per GPU (default); strong: 2^log2n signatures in total, split over the GPUs")
     ap.add_argument("--batch-log2n", type=int, default=None,
                     help="signatures per GPU of the batch side measurement (default 16 at 1 GPU = configs[3], "
                          "21 at N > 1 = configs[4]: 2^24 over 8 GPUs)")
@@ -231,7 +207,7 @@ def main():
     eng = sb.Engine(local)
     stream = torch.cuda.Stream(device=dev)
     eng.set_stream(stream.cuda_stream)
-    n = 1 << args.log2n
+    n = (1 << args.log2n) if args.scaling == "weak" else max(128, (1 << args.log2n) // world)
     L = args.msg_len
     seed = sb.synth.DEFAULT_SEED
 
@@ -332,6 +308,7 @@ def main():
     peak_w, peak_ms = eng.imad_peak(1 << 15)
     k_ms = float(np.mean(kernel_ms))
     achieved_w = n * w_per_verify(L) / (k_ms * 1e-3)
+    executed_w = n * cost_model.w_executed_fast(L) / (k_ms * 1e-3)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -339,21 +316,46 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_achieved = n * (HBM_BYTES_PER_VERIFY - 8 + L) / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "imad", "achieved": (achieved_w or 0) / 1e12, "peak": peak_w / 1e12, "unit": "Tmul32x32/s",
-                "frac": achieved_w / peak_w, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.log2n),
-                "frac_executed": n * (W_EXECUTED_FAST_L8 + (permutations_for(L) - 2) * W_EXECUTED_PER_PERMUTATION) / (k_ms * 1e-3) / peak_w,
+    hbm_achieved = n * cost_model.hbm_bytes_per_verify(L) / (k_ms * 1e-3) / 1e9
+    nominal = cost_model.nominal_peak_w_per_s(148, (clocks or {}).get("sm_max_mhz") or 1965.0)
+    # DRAM traffic / instruction counts of one launch come from the ncu capture committed under profiles/; they are only
+    # quoted when the capture was taken from the sources this library is built from
+    ncu = cost_model.ncu_constants() or {}
+    ncu_k = (ncu.get("k_verify_fast") or {}).get(str(args.log2n)) if n == (1 << args.log2n) else None
+    ncu_current = bool(ncu) and ncu.get("source_sha256") == cost_model.source_sha256()
+    roofline = {"bound": "imad", "achieved": achieved_w / 1e12, "peak": peak_w / 1e12, "unit": "Tmul32x32/s",
+                "frac": achieved_w / peak_w, "traffic": (ncu_k or {}).get("dram_bytes") if ncu_current else None,
+                "traffic_source": (ncu.get("capture") if ncu_k else None),
+                "traffic_capture_matches_sources": ncu_current if ncu_k else None,
+                "frac_executed": executed_w / peak_w,
+                "frac_vs_nominal": achieved_w / nominal, "frac_executed_vs_nominal": executed_w / nominal,
                 "kernel": "k_verify_fast", "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / dev_ms,
-                "peak_source": "measured live: schnorr_b200_imad_peak (K6, IMAD.WIDE.U32 chains, full grid)",
-                "peak_nominal": 148 * 32 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12 if True else None,
-                "algorithmic_units": "%d wide multiplies per verification (SURVEY.md 8d cost model v1, %d-byte message) x %d per launch" % (w_per_verify(L), L, n),
+                "peak_source": "measured live: schnorr_b200_imad_peak (K6, IMAD.WIDE.U32 chains, full grid), %.2f ms" % peak_ms,
+                "peak_nominal": nominal / 1e12,
+                "algorithmic_units": "%d wide multiplies per verification (cost_model.py = SURVEY.md 8d model v1, %d-byte message) x %d per launch" % (w_per_verify(L), L, n),
+                "executed_units": "%d wide multiplies per verification actually executed (host-build counter, cost_model.py)" % cost_model.w_executed_fast(L),
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    # ---- parity evidence gathered in this very run ----------------------------------------------------------------
+    parity = {"verdicts_equal_expected_pattern": int(n), "ranks": world}
+    if rank == 0:
+        import cref
+        rng = np.random.default_rng(5)
+        bad_idx = np.nonzero(expect)[0][:1024]
+        idx = np.unique(np.concatenate([rng.choice(n, min(n, 1024), replace=False), bad_idx]))
+        sub_blob = w["blob"].reshape(n, L)[idx].reshape(-1) if L else np.zeros(0, np.uint8)
+        sub_off = np.arange(len(idx) + 1, dtype=np.uint64) * np.uint64(L)
+        want = cref.verify_many(w["sigs"][idx], w["pk"][idx], w["inf"][idx], sub_blob, sub_off, cref.default_threads())
+        if not np.array_equal(want, got[idx]):
+            raise SystemExit("verdicts differ from the oracle on the sampled indices")
+        parity["verdicts_equal_oracle_on_sample"] = int(len(idx))
+        parity["sample"] = "1024 random indices + every injected fault (up to 1024), oracle/cref.c"
 
     # ---- side measurements (not part of the timed region) --------------------------------------
     extras = {}
     if not args.no_extras:
-        extras = side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_blob, d_off, hin, rank, world, dist)
+        extras = side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_blob, d_off, hin, rank, world, dist, parity)
 
     # ---- CPU baseline beside it (rank 0, N = 1) -------------------------------------------------
     cpu = None
@@ -370,24 +372,36 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u64 (Goldilocks Fp / Fp6 on 32-bit IMAD, exact)", "data": "synthetic",
-                "config": {"workload": "independent Signature::verify of 2^%d signatures per GPU, %d-byte messages, "
-                                       "1/1024 invalid injected (BASELINE configs[2])" % (args.log2n, L),
+                "config": {"workload": "independent Signature::verify of %s, %d-byte messages, "
+                                       "1/1024 invalid injected (BASELINE configs[2])" % (
+                                           ("2^%d signatures per GPU" % args.log2n) if args.scaling == "weak"
+                                           else ("2^%d signatures in total (%d per GPU)" % (args.log2n, n)), L),
                            "signatures_per_gpu": n, "msg_len": L, "parallelism": "shard%d (no data-path collective)" % world,
                            "l2_policy": "inputs (%.0f MB per GPU) larger than L2; no flush" % (n * (177 + L + 8) / 1e6)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "parity_checked": parity}
         line.update(extras)
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_blob, d_off, hin, rank, world, dist):
-    """hash_message throughput (configs[1]) and batch verification (configs[3]/[4]); device-timed."""
+def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_blob, d_off, hin, rank, world, dist, parity):
+    """hash_message throughput (configs[1]), batch verification (configs[3]/[4]), strong scaling of configs[2], the
+    one-process multi-GPU arm of the C ABI and the small-call latencies; device-timed, outside the headline region."""
+    import schnorr_sig_b200 as sb
     out = {}
     L = args.msg_len
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # K1: hash sweep point at n messages
     d_rx = d_sigs[:, :48].contiguous()
     d_dig = torch.empty((n, 32), dtype=torch.uint8, device=dev)
@@ -402,78 +416,174 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
     peak_w, _ = eng.imad_peak(1 << 15)
     out["hash"] = {"metric": "rescue_hash_message_per_sec", "value": world * n / (hms * 1e-3), "n_per_gpu": n, "msg_len": L,
                    "ms": hms, "roofline_frac_imad": (n * w_per_hash(L) / (hms * 1e-3)) / peak_w}
+
     # K3/K4: one batch of nb signatures per GPU, partial MSM per rank + one small gather + finish on rank 0
-    import schnorr_sig_b200 as sb
     blog = args.batch_log2n if args.batch_log2n is not None else (16 if world == 1 else 21)
     nb = 1 << blog
     bin_ = hin if nb <= n else sb.synth.host_inputs(sb.synth.DEFAULT_SEED + 1, nb, L, shard=rank)
-    h_rand = bin_["rand"][:nb]
-    with torch.cuda.stream(stream):
-        d_sk = torch.from_numpy(bin_["sk"][:nb]).to(dev)
-        d_nonce = torch.from_numpy(bin_["nonce"][:nb]).to(dev)
-        gb = torch.from_numpy(bin_["blob"][:nb * L]).to(dev) if L else torch.zeros(16, dtype=torch.uint8, device=dev)
-        goff = torch.from_numpy(bin_["off"][:nb + 1].view(np.int64)).to(dev)
-        gpk = torch.empty((nb, 96), dtype=torch.uint8, device=dev)
-        ginf = torch.zeros(nb, dtype=torch.uint8, device=dev)
-        gsig = torch.empty((nb, 81), dtype=torch.uint8, device=dev)
-        eng.keygen_dev(nb, d_sk, gpk, ginf)
-        eng.sign_many_dev(nb, d_sk, gpk, ginf, gb, goff, d_nonce, gsig)
-        d_rand = torch.from_numpy(h_rand).to(dev)
-        part = torch.zeros(192, dtype=torch.uint8, device=dev)
-        res = torch.zeros(216, dtype=torch.uint8, device=dev)
 
-        def batch_once():
-            eng.batch_partial_dev(nb, gsig, gpk, ginf, gb, goff, d_rand, part)
-            if dist is not None:
-                allp = torch.zeros((world, 192), dtype=torch.uint8, device=dev)
-                stream.synchronize()
-                dist.all_gather_into_tensor(allp, part)
-                torch.cuda.current_stream(dev).synchronize()
-            else:
-                allp = part.view(1, 192)
-            if rank == 0:
-                eng.batch_finish_dev(world, allp, res)
+    def device_batch(inputs, count):
+        """device-resident keys / signatures / randomisers for `count` signatures of `inputs`"""
+        with torch.cuda.stream(stream):
+            d_sk = torch.from_numpy(inputs["sk"][:count]).to(dev)
+            d_nonce = torch.from_numpy(inputs["nonce"][:count]).to(dev)
+            gb = torch.from_numpy(inputs["blob"][:count * L]).to(dev) if L else torch.zeros(16, dtype=torch.uint8, device=dev)
+            goff = torch.from_numpy(inputs["off"][:count + 1].view(np.int64)).to(dev)
+            gpk = torch.empty((count, 96), dtype=torch.uint8, device=dev)
+            ginf = torch.zeros(count, dtype=torch.uint8, device=dev)
+            gsig = torch.empty((count, 81), dtype=torch.uint8, device=dev)
+            eng.keygen_dev(count, d_sk, gpk, ginf)
+            eng.sign_many_dev(count, d_sk, gpk, ginf, gb, goff, d_nonce, gsig)
+            d_rand = torch.from_numpy(inputs["rand"][:count]).to(dev)
             stream.synchronize()
+        return gsig, gpk, ginf, gb, goff, d_rand
 
-        batch_once()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        batch_once()
-        b.record(stream)
-        stream.synchronize()
-        wall = time.perf_counter() - t0
-    bms = max(a.elapsed_time(b), wall * 1e3) if dist is not None else a.elapsed_time(b)
-    t = torch.tensor([bms], dtype=torch.float64, device=dev)
+    part = torch.zeros(192, dtype=torch.uint8, device=dev)
+    res = torch.zeros(216, dtype=torch.uint8, device=dev)
+    allp = torch.zeros((world, 192), dtype=torch.uint8, device=dev)
+
+    def batch_once(bufs, count):
+        """this rank's partial -> ONE all_gather of 192 bytes per rank, enqueued on the engine's stream right behind the
+        partial kernels (no host synchronisation around it) -> finish on rank 0"""
+        gsig, gpk, ginf, gb, goff, d_rand = bufs
+        with torch.cuda.stream(stream):
+            eng.batch_partial_dev(count, gsig, gpk, ginf, gb, goff, d_rand, part)
+            if dist is not None:
+                dist.all_gather_into_tensor(allp, part)
+                gathered = allp
+            else:
+                gathered = part.view(1, 192)
+            if rank == 0:
+                eng.batch_finish_dev(world, gathered, res)
+
+    bufs = device_batch(bin_, nb)
+    batch_once(bufs, nb)
+    stream.synchronize()
+    torch.cuda.synchronize(dev)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    bms = float(t.item())
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    batch_once(bufs, nb)
+    b.record(stream)
+    stream.synchronize()
+    bms = max_over_ranks(a.elapsed_time(b))
+    plan = eng.last_batch_plan()
     verdict = int(res[0].item()) if rank == 0 else None
     # invalid-signature injection (SURVEY.md 8d C4/C5): one corrupted signature on the LAST rank must fail the lot
-    with torch.cuda.stream(stream):
-        if rank == world - 1:
-            gsig[nb // 2, 49] ^= 1
-        batch_once()
-        torch.cuda.synchronize(dev)
+    if rank == world - 1:
+        bufs[0][nb // 2, 49] ^= 1
+    batch_once(bufs, nb)
+    stream.synchronize()
+    torch.cuda.synchronize(dev)
     verdict_bad = int(res[0].item()) if rank == 0 else None
+    w_sig = cost_model.w_per_batch_signature(nb, L, plan[:3])
     out["batch"] = {"metric": "schnorr_batch_verified_signatures_per_sec", "value": world * nb / (bms * 1e-3),
                     "signatures_per_gpu": nb, "ms": bms, "verdict": verdict,
                     "verdict_with_one_corrupted_signature_on_last_rank": verdict_bad,
-                    "roofline_frac_imad": (nb * (W_PER_BATCH_SIG + (permutations_for(L) - 2) * W_PER_PERMUTATION) / (bms * 1e-3)) / peak_w,
-                    "exchange": "one all_gather of 192 B per rank" if world > 1 else "none (1 GPU)"}
+                    "plan": {"window_bits": plan[0], "windows": plan[1], "buckets_per_window": plan[2], "segment_len": plan[3]},
+                    "canonical_w_per_signature": w_sig,
+                    "roofline_frac_imad": (nb * w_sig / (bms * 1e-3)) / peak_w,
+                    "exchange": "one all_gather of 192 B per rank on the compute stream" if world > 1 else "none (1 GPU)"}
     if rank == 0 and (verdict != 0 or verdict_bad != 2):
         raise SystemExit("batch verification returned verdicts %r / %r (expected 0 / 2)" % (verdict, verdict_bad))
+
+    # sharded batch against the oracle (configs[4] in miniature): 4096 signatures cut over the ranks; rank 0's finished
+    # points must equal a single-GPU run over the concatenated shards and oracle/cref.c; an invalid signature on the last
+    # rank must turn the verdict into Err
+    ns = 4096
+    small = sb.synth.host_inputs(sb.synth.DEFAULT_SEED + 99, ns, L, shard=0)     # the same inputs on every rank
+    lo, hi = (ns * rank) // world, (ns * (rank + 1)) // world
+    sl = {k: small[k][lo:hi] for k in ("sk", "nonce", "rand")}
+    sl["blob"] = small["blob"][lo * L:hi * L]
+    sl["off"] = small["off"][lo:hi + 1] - small["off"][lo]
+    sbufs = device_batch(sl, hi - lo)
+    batch_once(sbufs, hi - lo)
+    stream.synchronize()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        import cref
+        got = res.cpu().numpy().copy()
+        pk_s, inf_s = eng.keygen(small["sk"])
+        sig_s = eng.sign_many(small["sk"], pk_s, inf_s, small["blob"], small["off"], small["nonce"])
+        v1, l1, r1 = eng.verify_batch(sig_s, pk_s, inf_s, small["blob"], small["off"], small["rand"])
+        cv, cl, cr = cref.verify_batch(sig_s, pk_s, inf_s, small["blob"], small["off"], small["rand"], cref.default_threads())
+        same = (got[0] == v1 == cv == 0 and np.array_equal(got[8:105], l1) and np.array_equal(got[8:105], cl)
+                and np.array_equal(got[112:209], r1) and np.array_equal(got[112:209], cr))
+        if not same:
+            raise SystemExit("sharded batch over %d ranks differs from the single-GPU run / the oracle" % world)
+    if rank == world - 1:
+        sbufs[0][(hi - lo) // 2, 49] ^= 1
+    batch_once(sbufs, hi - lo)
+    stream.synchronize()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        if int(res[0].item()) != 2:
+            raise SystemExit("sharded batch with an injected invalid signature returned %d" % int(res[0].item()))
+        parity["sharded_batch_points_equal_single_gpu_and_oracle"] = {"signatures": ns, "ranks": world, "injected_invalid_verdict": 2}
+
+    # strong scaling of configs[2]: the SAME 2^log2n signatures in total, cut over the ranks (131 072 per GPU at N = 8:
+    # 3.46 kernel waves)
+    if args.scaling == "weak" and world > 1:
+        m = max(128, n // world)
+        with torch.cuda.stream(stream):
+            v_s = torch.full((m,), 255, dtype=torch.uint8, device=dev)
+            eng.verify_many_dev(m, d_sigs, d_pk, d_inf, d_blob, d_off, v_s)
+            stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            eng.verify_many_dev(m, d_sigs, d_pk, d_inf, d_blob, d_off, v_s)
+        b.record(stream)
+        stream.synchronize()
+        sms = max_over_ranks(a.elapsed_time(b)) / args.steps
+        out["strong_scaling"] = {"metric": METRIC, "value": world * m / (sms * 1e-3), "signatures_total": world * m,
+                                 "signatures_per_gpu": m, "ms_per_step": sms, "n_gpus": world}
+
+    # one process driving every GPU through the C ABI (schnorr_b200_create_multi): host buffers in, verdicts out.
+    # Rank 0 only, while the other ranks idle at the barrier below.
+    if dist is not None:
+        dist.barrier()
+    if rank == 0 and torch.cuda.device_count() >= world:
+        me = sb.Engine(list(range(world)))
+        try:
+            w_sigs, w_pk, w_inf = d_sigs.cpu().numpy(), d_pk.cpu().numpy(), d_inf.cpu().numpy()
+            w_blob = d_blob.cpu().numpy()[:n * L]
+            reps = world
+            hs = torch.from_numpy(np.tile(w_sigs, (reps, 1))).pin_memory()
+            hp = torch.from_numpy(np.tile(w_pk, (reps, 1))).pin_memory()
+            hi_ = torch.from_numpy(np.tile(w_inf, reps)).pin_memory()
+            hb = torch.from_numpy(np.tile(w_blob, reps) if L else np.zeros(16, np.uint8)).pin_memory()
+            ho = torch.from_numpy((np.arange(reps * n + 1, dtype=np.uint64) * np.uint64(L)).view(np.int64)).pin_memory()
+            hv = torch.full((reps * n,), 255, dtype=torch.uint8).pin_memory()
+            me.verify_many_raw(reps * n, hs, hp, hi_, hb, ho, hv)
+            ref = hv.numpy()[:n].copy()
+            ok = all(np.array_equal(hv.numpy()[k * n:(k + 1) * n], ref) for k in range(reps))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                me.verify_many_raw(reps * n, hs, hp, hi_, hb, ho, hv)
+            dt = (time.perf_counter() - t0) / args.steps
+            out["e2e_one_process"] = {"value": reps * n / dt, "unit": UNIT, "devices": world, "ms_per_step": dt * 1e3,
+                                      "signatures_per_step": reps * n, "verdicts_consistent_across_devices": bool(ok),
+                                      "api": "schnorr_b200_create_multi + schnorr_b200_verify_many (pinned host buffers, "
+                                             "one host thread per device, copies inside the call, wall clock)"}
+        finally:
+            me.close()
+    if dist is not None:
+        dist.barrier()
+
     # small calls through the host API (the reference's own Criterion case is ONE verify, benches/schnorr.rs:60-77):
     # host buffers in, verdicts out, wall clock around the call; rank 0 only
     if rank == 0:
-        small = {}
-        for ns in (1, 1024):
+        small_calls = {}
+        for ns_ in (1, 1024):
             hs = {k: hin[k] for k in ("sk", "nonce", "blob", "off")}
-            pk_s, inf_s = eng.keygen(hs["sk"][:ns])
-            off_s = hs["off"][:ns + 1].copy()
+            pk_s, inf_s = eng.keygen(hs["sk"][:ns_])
+            off_s = hs["off"][:ns_ + 1].copy()
             blob_s = hs["blob"][:int(off_s[-1])] if int(off_s[-1]) else np.zeros(0, np.uint8)
-            sig_s = eng.sign_many(hs["sk"][:ns], pk_s, inf_s, blob_s, off_s, hs["nonce"][:ns])
+            sig_s = eng.sign_many(hs["sk"][:ns_], pk_s, inf_s, blob_s, off_s, hs["nonce"][:ns_])
             v = eng.verify_many(sig_s, pk_s, inf_s, blob_s, off_s)
             if int(v.max()) != 0:
                 raise SystemExit("small-call verification failed")
@@ -482,9 +592,9 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
                 t0 = time.perf_counter()
                 eng.verify_many(sig_s, pk_s, inf_s, blob_s, off_s)
                 ts.append(time.perf_counter() - t0)
-            small["n%d_ms" % ns] = float(np.mean(ts)) * 1e3
-        small["kernel"] = "k_verify_dist (one signature per six lanes)"
-        out["small_calls"] = small
+            small_calls["n%d_ms" % ns_] = float(np.mean(ts)) * 1e3
+        small_calls["kernel"] = "k_verify_dist (one signature per six lanes)"
+        out["small_calls"] = small_calls
     return out
 
 

@@ -84,6 +84,9 @@ int schnorr_b200_set_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures
 /* Test hook: force the Pippenger window width (4..16, 0 = planner's choice) and the segment length of the bucket
  * accumulation (>= 8, 0 = automatic) of the batch path, to exercise the skewed-bucket code paths. */
 int schnorr_b200_set_msm_geometry(schnorr_b200_ctx *ctx, int window_bits, unsigned segment_len);
+/* Pippenger geometry of the last batch call on this context (window width c, number of windows K, entries per
+ * accumulation segment): the unit count of the batch roofline is computed from the plan actually used (cost_model.py). */
+int schnorr_b200_last_batch_plan(const schnorr_b200_ctx *ctx, int *window_bits, int *windows, unsigned *segment_len);
 
 /* hash_message(&Fp6, &PublicKey, &[u8]) -> [u8; 32]            src/signature.rs:274-306
  * rx48: n x 48 B (R.x limbs), pk96: n x 96 B, digests: n x 32 B.  */

@@ -705,6 +705,9 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     while (T > 8 && max_entries / T < 65536) T /= 2;
     if (ctx->msm_t_override) T = ctx->msm_t_override;  // schnorr_b200_set_msm_geometry (tests)
     while ((max_entries + T - 1) / T > ((size_t)1 << 20)) T *= 2;
+    ctx->last_msm_c = pl.c;
+    ctx->last_msm_K = pl.K;
+    ctx->last_msm_T = T;
     size_t nseg = ((max_entries + T - 1) / T + 127) / 128 * 128;
     void* d_parts;
     size_t max_long = nseg / MSM_LONG_SPAN + 1;  // buckets that can span >= MSM_LONG_SPAN segments

@@ -47,6 +47,8 @@ struct schnorr_b200_ctx {
     bool exact_only = false;                        // schnorr_b200_set_exact_only: skip the fast path (A/B measurements, tests)
     int msm_c_override = 0;                         // schnorr_b200_set_msm_geometry (tests): forced window width / segment length
     uint32_t msm_t_override = 0;
+    int last_msm_c = 0, last_msm_K = 0;             // Pippenger geometry of the last batch call (schnorr_b200_last_batch_plan)
+    uint32_t last_msm_T = 0;
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
@@ -860,6 +862,14 @@ int schnorr_b200_set_msm_geometry(schnorr_b200_ctx* ctx, int window_bits, unsign
         sh->msm_c_override = window_bits;
         sh->msm_t_override = segment_len;
     }
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_last_batch_plan(const schnorr_b200_ctx* ctx, int* window_bits, int* windows, unsigned* segment_len) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    const schnorr_b200_ctx* c = ctx->shards.empty() ? ctx : ctx->shards[0];
+    if (window_bits) *window_bits = c->last_msm_c;
+    if (windows) *windows = c->last_msm_K;
+    if (segment_len) *segment_len = c->last_msm_T;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_last_exact_count(schnorr_b200_ctx* ctx, uint64_t* count) {

@@ -104,6 +104,12 @@ class Engine:
         """Test hook: force the Pippenger window width / segment length of the batch path (0 = automatic)."""
         self._check(self._L.schnorr_b200_set_msm_geometry(self._h, int(window_bits), int(segment_len)), "set_msm_geometry")
 
+    def last_batch_plan(self):
+        """(window bits c, windows K, buckets per window B, segment length T) of the last batch call."""
+        c, k, t = C.c_int(0), C.c_int(0), C.c_uint(0)
+        self._check(self._L.schnorr_b200_last_batch_plan(self._h, C.byref(c), C.byref(k), C.byref(t)), "last_batch_plan")
+        return c.value, k.value, (1 << (c.value - 1)) if c.value else 0, t.value
+
     def set_dist_threshold(self, max_signatures: int):
         """Calls up to this many signatures use the six-lanes-per-signature kernel (0 = never, 2**62 = always)."""
         self._check(self._L.schnorr_b200_set_dist_threshold(self._h, int(max_signatures)), "set_dist_threshold")

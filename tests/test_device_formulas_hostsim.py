@@ -377,8 +377,12 @@ def test_executed_multiply_counts_match_design_doc(hostsim):
         mb = np.frombuffer(w["msgs"][0], dtype=np.uint8).copy()
         assert fn(0, mb, w["msgs"][0]) == 0
         counts[name] = hostsim.hs_wide_count_reset()
-    assert 300_000 < counts["fast"] < 380_000, counts       # ~0.34 M multiplies per verification
-    assert 500_000 < counts["exact"] < 560_000, counts      # ~0.53 M (exact Jacobian kernel)
+    import cost_model
+    # the executed-multiply figures behind roofline.frac_executed (cost_model.py is their single source)
+    assert counts["fast"] == cost_model.W_EXECUTED_FAST_L8, counts
+    assert counts["exact"] == cost_model.W_EXECUTED_EXACT_L8, counts
+    assert cost_model.w_per_verify(8) == 787338 and cost_model.w_per_verify(80) == 843618
+    assert cost_model.w_per_hash(8) == 56280 and cost_model.permutations_for(160) == 5
     print(counts)
 
 
