@@ -543,9 +543,13 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
                                  "signatures_per_gpu": m, "ms_per_step": sms, "n_gpus": world}
 
     # one process driving every GPU through the C ABI (schnorr_b200_create_multi): host buffers in, verdicts out.
-    # Rank 0 only, while the other ranks idle at the barrier below.
+    # Rank 0 only; the other ranks wait on a HOST-side (gloo) barrier -- an NCCL barrier would keep a spinning kernel on
+    # their GPUs, which rank 0's kernels would have to time-slice with.
+    cpu_group = None
     if dist is not None:
-        dist.barrier()
+        torch.cuda.synchronize(dev)
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
     if rank == 0 and torch.cuda.device_count() >= world:
         me = sb.Engine(list(range(world)))
         try:
@@ -572,7 +576,7 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
         finally:
             me.close()
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     # small calls through the host API (the reference's own Criterion case is ONE verify, benches/schnorr.rs:60-77):
     # host buffers in, verdicts out, wall clock around the call; rank 0 only

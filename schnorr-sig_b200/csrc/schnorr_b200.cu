@@ -44,6 +44,8 @@ struct schnorr_b200_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the dominant kernel of the last call
     size_t verify_wave = 148 * 256;                 // signatures resident at once in k_verify (filled at creation)
     cudaStream_t copy_stream = nullptr;             // host->device staging of the pipelined host entry points
+    cudaStream_t aux_stream = nullptr;              // second compute stream: consecutive pipeline chunks alternate between
+    cudaEvent_t ev_aux = nullptr;                   // the two, so a chunk's blocks fill the SMs the previous chunk drains
     bool exact_only = false;                        // schnorr_b200_set_exact_only: skip the fast path (A/B measurements, tests)
     int msm_c_override = 0;                         // schnorr_b200_set_msm_geometry (tests): forced window width / segment length
     uint32_t msm_t_override = 0;
@@ -736,6 +738,8 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
         ctx->verify_wave = (size_t)ctx->sm_count * per_sm * VERIFY_THREADS;
     }
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     for (int c = 0; c < schnorr_b200_ctx::MAX_CHUNKS; c++) CREATE_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreate(&ctx->ev_k0));
     CREATE_TRY(cudaEventCreate(&ctx->ev_k1));
@@ -797,6 +801,8 @@ void schnorr_b200_destroy(schnorr_b200_ctx* ctx) {
     for (int c = 0; c < schnorr_b200_ctx::MAX_CHUNKS; c++)
         if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -990,10 +996,12 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         bounds[k + 1] = n;
         chunks = k + 1;
     }
-    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
-    // the copy stream must not overtake work of a previous call that still reads the scratch buffers
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream, ks2 = ctx->aux_stream;
+    // neither the copy stream nor the second compute stream may overtake work of a previous call that still reads the
+    // scratch buffers
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[0], ks));
     CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[0], 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ks2, ctx->ev_chunk[0], 0));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, cs));
     for (int c = 0; c < chunks; c++) {
         size_t lo = bounds[c], hi = bounds[c + 1], cn = hi - lo;
@@ -1003,18 +1011,25 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         size_t b0 = msg_off[lo], b1 = msg_off[hi];
         if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_m + b0, msgs + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[c], cs));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ks, ctx->ev_chunk[c], 0));
+        // consecutive chunks run on alternating compute streams: the blocks of chunk c + 1 start on the SMs that chunk c
+        // is draining instead of waiting for its last block (chunks touch disjoint regions of every buffer)
+        cudaStream_t st = (c & 1) ? ks2 : ks;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
         soa_batch sc;
         sc.planes = soa.planes + (size_t)SOA_PLANES * lo;   // a private [11][cn] region per chunk
         sc.flags = soa.flags + lo;
         sc.sig_flag = soa.sig_flag + lo;
         sc.n = cn;
-        k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, ks>>>(cn, (uint8_t*)d_sig + 81 * lo, (uint8_t*)d_pk + 96 * lo,
+        k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, st>>>(cn, (uint8_t*)d_sig + 81 * lo, (uint8_t*)d_pk + 96 * lo,
                                                                          pk_inf ? (uint8_t*)d_inf + lo : nullptr, sc);
-        cudaEventRecord(ctx->ev_k0, ks);
-        if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, ks)) return rc;
-        cudaEventRecord(ctx->ev_k1, ks);
+        if (st == ks) cudaEventRecord(ctx->ev_k0, ks);
+        if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, st)) return rc;
+        if (st == ks) cudaEventRecord(ctx->ev_k1, ks);
         ctx->launches += 1;
+    }
+    if (chunks > 1) {  // the main stream continues after the second one
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux, ks2));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ks, ctx->ev_aux, 0));
     }
     // verdicts come back after EVERY chunk has been enqueued: a device-to-host copy into pageable memory blocks the
     // host until the kernels before it have finished, which would serialise the pipeline above (1 byte per signature:
