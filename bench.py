@@ -446,6 +446,9 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
         """this rank's partial -> ONE all_gather of 192 bytes per rank, enqueued on the engine's stream right behind the
         partial kernels (no host synchronisation around it) -> finish on rank 0"""
         gsig, gpk, ginf, gb, goff, d_rand = bufs
+        if dist is None:   # one GPU: the whole batch as one enqueue ((sum s e) G runs beside the MSM)
+            eng.verify_batch_dev(count, gsig, gpk, ginf, gb, goff, d_rand, res)
+            return
         with torch.cuda.stream(stream):
             eng.batch_partial_dev(count, gsig, gpk, ginf, gb, goff, d_rand, part)
             if dist is not None:

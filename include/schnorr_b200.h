@@ -121,6 +121,11 @@ int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx *ctx, size_t n, const ui
 int schnorr_b200_verify_batch(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
                               const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
                               const uint8_t *rand32, int *verdict, uint8_t *lhs97, uint8_t *rhs97);
+/* Same on DEVICE buffers (single-device context): enqueues the whole batch -- partial MSM, (sum s_i e_i) G on a second
+ * stream beside it, finish -- and does not synchronise.  result216 (device): verdict(1) pad(7) lhs97 pad(7) rhs97 pad(7). */
+int schnorr_b200_verify_batch_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,
+                                  const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
+                                  const uint8_t *rand32, uint8_t *result216);
 /* Multi-GPU form: each rank reduces its slice to one 192-byte partial (device buffer), the caller
  * gathers the partials (one small NCCL gather) and any rank finishes.  */
 int schnorr_b200_batch_partial_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *sigs81, const uint8_t *pk96,

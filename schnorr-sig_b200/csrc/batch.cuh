@@ -194,32 +194,57 @@ __global__ void __launch_bounds__(256) k_msm_count(const uint32_t* __restrict__ 
     }
 }
 
-// single-block exclusive scan of m counters (m up to a few million): offsets[i] = sum counts[< i]
-__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ counts, size_t m,
-                                                         uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t sh[1024];
-    __shared__ uint32_t carry_sh;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    size_t per = (m + 1023) / 1024;
-    size_t lo = (size_t)threadIdx.x * per, hi = lo + per < m ? lo + per : m;
-    uint32_t sum = 0;
-    for (size_t i = lo; i < hi; i++) sum += counts[i];
+// Exclusive scan of m counters (m = windows x (buckets + 1), up to a few million) in two grid-wide passes:
+//   k_scan_local   every block scans its tile of SCAN_TILE counters in place (exclusive, relative to the tile) and
+//                  records the tile total
+//   k_scan_offsets every block adds the sum of the totals of the tiles before it (<= a few hundred values: one
+//                  strided sum + a block reduction) to its tile
+// (the single-block version took 82 us of a 3 ms batch at 2^16 signatures.)
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_PER_THREAD = 8;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const uint32_t* __restrict__ counts, size_t m,
+                                                             uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_total) {
+    __shared__ uint32_t sh[SCAN_THREADS];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        v[k] = base + k < m ? counts[base + k] : 0;
+        sum += v[k];
+    }
     sh[threadIdx.x] = sum;
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t v = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
+    for (int d = 1; d < SCAN_THREADS; d <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+        uint32_t t = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0;
         __syncthreads();
-        sh[threadIdx.x] += v;
+        sh[threadIdx.x] += t;
         __syncthreads();
     }
     uint32_t run = sh[threadIdx.x] - sum;
-    for (size_t i = lo; i < hi; i++) {
-        uint32_t c = counts[i];
-        offsets[i] = run;
-        run += c;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        if (base + k < m) offsets[base + k] = run;
+        run += v[k];
     }
+    if (threadIdx.x == SCAN_THREADS - 1) tile_total[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_offsets(size_t m, uint32_t* __restrict__ offsets,
+                                                               const uint32_t* __restrict__ tile_total) {
+    __shared__ uint32_t sh[SCAN_THREADS];
+    uint32_t part = 0;
+    for (unsigned t = threadIdx.x; t < blockIdx.x; t += SCAN_THREADS) part += tile_total[t];
+    sh[threadIdx.x] = part;
+    __syncthreads();
+    for (int d = SCAN_THREADS / 2; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    uint32_t add = sh[0];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++)
+        if (base + k < m) offsets[base + k] += add;
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint32_t* __restrict__ scalars, size_t npts, msm_plan pl,
@@ -279,7 +304,7 @@ __device__ __forceinline__ jf_pt load_jac_as_jf(const jac_pt* in) {
     return r;
 }
 __device__ __forceinline__ jf_pt jf_identity() { return jf_pt{fp6_one(), fp6_one(), 0}; }
-__global__ void __launch_bounds__(128) k_msm_segment_sum(const uint64_t* __restrict__ pts, msm_plan pl, uint32_t nslots,
+__global__ void __launch_bounds__(128, 3) k_msm_segment_sum(const uint64_t* __restrict__ pts, msm_plan pl, uint32_t nslots,
                                                          uint32_t T, const uint32_t* __restrict__ offsets,
                                                          const uint32_t* __restrict__ counts,
                                                          const uint32_t* __restrict__ sorted, jac_pt* __restrict__ buckets,
@@ -591,23 +616,11 @@ __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, const jac_pt* __
     partial[23] = 0;
 }
 
-// result200: [0] verdict, [8..105) lhs97, [104..201)... laid out as verdict(1) pad(7) lhs(97) pad(7) rhs(97)
-static constexpr size_t RESULT_BYTES = 216;
-// One warp.  (sum lin) G is a sum of 20 table points (fixed-base windows): lane i fetches the point of window i and a
-// shuffle tree of exact (X, Y, w) additions folds them in 5 steps instead of 20 serial mixed additions; its
-// denominator lies in Fp, so the affine form needs an Fp inversion only.  Lane 0 adds the per-GPU partials meanwhile.
-__global__ void __launch_bounds__(32) k_batch_finish(size_t np, const uint64_t* __restrict__ partials,
-                                                      const uint64_t* __restrict__ gtab, uint8_t* __restrict__ result) {
-    if (blockIdx.x != 0) return;
-    int lane = threadIdx.x;
-    scalar lin = sc_zero();
-    bool bad = false;
-    for (size_t r = 0; r < np; r++) {  // every lane: 32-byte scalars, cheap
-        const uint64_t* p = partials + r * 24;
-        lin = sc_add(lin, sc_from_u64x4(p[18], p[19], p[20], p[21]));
-        bad |= p[22] != 0;
-    }
-    // lane i < 20: +-d_i 2^(13 i) G from the table (digits recoded as in fixed_base_accumulate)
+// lin * G on ONE WARP: lane i fetches the table point of window i (digits recoded as in fixed_base_accumulate), a
+// shuffle tree of exact (X, Y, w) additions folds the 20 points in 5 steps, lane 0 normalises with one Fp inversion.
+// Valid on lane 0 only.
+__device__ __forceinline__ void warp_fixed_base_affine(const scalar& lin, const uint64_t* __restrict__ gtab, int lane,
+                                                       fp6& rx, fp6& ry, bool& rinf) {
     jf_pt t = jf_identity();
     {
         int carry = 0, my_d = 0;
@@ -634,14 +647,64 @@ __global__ void __launch_bounds__(32) k_batch_finish(size_t np, const uint64_t* 
         if (lane + d >= 32) o.w = 0;
         jf_add_exact(&t, &o);
     }
-    if (lane != 0) return;
-    fp6 rx = fp6_zero(), ry = fp6_zero();
-    bool rinf = t.w == 0;
-    if (!rinf) {
+    rx = fp6_zero();
+    ry = fp6_zero();
+    rinf = t.w == 0;
+    if (lane == 0 && !rinf) {
         fp_t wi = fp_inv(t.w), wi2 = fp_sqr(wi);
         rx = fp6_scale(t.X, wi2);
         ry = fp6_scale(t.Y, fp_mul(wi2, wi));
     }
+}
+// (sum s_i e_i) G of a SINGLE-device batch, launched on the second stream as soon as the scalar sum is known, so that it
+// runs beside the MSM instead of behind it: rhs13 = x (6) | y (6) | infinity flag
+__global__ void __launch_bounds__(32) k_lin_times_g(const uint32_t* __restrict__ lin8, const uint64_t* __restrict__ gtab,
+                                                     uint64_t* __restrict__ rhs13) {
+    if (blockIdx.x != 0) return;
+    int lane = threadIdx.x;
+    scalar lin;
+#pragma unroll
+    for (int k = 0; k < 8; k++) lin.l[k] = lin8[k];
+    fp6 rx, ry;
+    bool rinf;
+    warp_fixed_base_affine(lin, gtab, lane, rx, ry, rinf);
+    if (lane != 0) return;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        rhs13[c] = rx.c[c];
+        rhs13[6 + c] = ry.c[c];
+    }
+    rhs13[12] = rinf ? 1 : 0;
+}
+
+// result200: [0] verdict, [8..105) lhs97, [104..201)... laid out as verdict(1) pad(7) lhs(97) pad(7) rhs(97)
+static constexpr size_t RESULT_BYTES = 216;
+// One warp: adds the per-GPU partials, (sum lin) G (unless `rhs_pre` already holds it), x-only comparison.
+__global__ void __launch_bounds__(32) k_batch_finish(size_t np, const uint64_t* __restrict__ partials,
+                                                      const uint64_t* __restrict__ gtab, uint8_t* __restrict__ result,
+                                                      const uint64_t* __restrict__ rhs_pre) {
+    if (blockIdx.x != 0) return;
+    int lane = threadIdx.x;
+    scalar lin = sc_zero();
+    bool bad = false;
+    for (size_t r = 0; r < np; r++) {  // every lane: 32-byte scalars, cheap
+        const uint64_t* p = partials + r * 24;
+        lin = sc_add(lin, sc_from_u64x4(p[18], p[19], p[20], p[21]));
+        bad |= p[22] != 0;
+    }
+    fp6 rx, ry;
+    bool rinf;
+    if (rhs_pre) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            rx.c[c] = rhs_pre[c];
+            ry.c[c] = rhs_pre[6 + c];
+        }
+        rinf = rhs_pre[12] != 0;
+    } else {
+        warp_fixed_base_affine(lin, gtab, lane, rx, ry, rinf);
+    }
+    if (lane != 0) return;
     jac_pt acc = jac_identity();
     for (size_t r = 0; r < np; r++) {
         const uint64_t* p = partials + r * 24;
@@ -673,9 +736,11 @@ __global__ void __launch_bounds__(32) k_batch_finish(size_t np, const uint64_t* 
 }
 
 // ---- host orchestration ----------------------------------------------------------------------
+// rhs_pre (optional, device, 13 x u64): single-device batches get (sum s_i e_i) G computed on the second stream beside the
+// MSM; the caller's finish kernel must wait on ctx->ev_aux
 static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                               const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
-                              const uint8_t* rand32, uint8_t* partial192) {
+                              const uint8_t* rand32, uint8_t* partial192, uint64_t* rhs_pre = nullptr) {
     soa_batch soa;
     if (int rc = alloc_soa(ctx, n, &soa)) return rc;
     size_t npts = 2 * n;
@@ -693,7 +758,8 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     if (int rc = ensure_scratch(ctx, SL_D, npts * 96, &d_pts)) return rc;
     if (int rc = ensure_scratch(ctx, SL_E, npts * 32, &d_sc)) return rc;
     if (int rc = ensure_scratch(ctx, SL_F, n * 32 + 512 * 32, &d_lin)) return rc;
-    if (int rc = ensure_scratch(ctx, SL_G, nslots * 4 * 3, &d_cnt)) return rc;
+    size_t scan_tiles_max = (nslots + SCAN_TILE - 1) / SCAN_TILE;
+    if (int rc = ensure_scratch(ctx, SL_G, nslots * 4 * 3 + 4 * scan_tiles_max + 64, &d_cnt)) return rc;
     if (int rc = ensure_scratch(ctx, SL_J, npts * pl.K * 4, &d_sorted)) return rc;
     if (int rc = ensure_scratch(ctx, SL_K, sizeof(jac_pt) * ((size_t)pl.K * pl.B + (size_t)pl.K * pl.chunks + pl.K), &d_buckets))
         return rc;
@@ -717,6 +783,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     uint32_t* counts = (uint32_t*)d_cnt;
     uint32_t* offsets = counts + nslots;
     uint32_t* cursor = offsets + nslots;
+    uint32_t* tile_total = cursor + nslots;   // one total per scan tile (written before it is read: no clearing needed)
     jac_pt* buckets = (jac_pt*)d_buckets;
     jac_pt* chunk_out = buckets + (size_t)pl.K * pl.B;
     jac_pt* windows = chunk_out + (size_t)pl.K * pl.chunks;
@@ -740,8 +807,17 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     if (sum_blocks > 256) sum_blocks = 256;
     k_scalar_sum<<<sum_blocks, 256, 0, st>>>(lin, n, lin_part);
     k_scalar_sum<<<1, 256, 0, st>>>(lin_part, (size_t)sum_blocks, lin_total);
+    if (rhs_pre) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[1], st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chunk[1], 0));
+        k_lin_times_g<<<1, 32, 0, ctx->aux_stream>>>(lin_total, ctx->gtab, rhs_pre);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
+        ctx->launches += 1;
+    }
     k_msm_count<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, counts);
-    k_exclusive_scan<<<1, 1024, 0, st>>>(counts, nslots, offsets);
+    unsigned scan_tiles = (unsigned)((nslots + SCAN_TILE - 1) / SCAN_TILE);
+    k_scan_local<<<scan_tiles, SCAN_THREADS, 0, st>>>(counts, nslots, offsets, tile_total);
+    k_scan_offsets<<<scan_tiles, SCAN_THREADS, 0, st>>>(nslots, offsets, tile_total);
     k_msm_scatter<<<grid_for(npts, 256), 256, 0, st>>>((uint32_t*)d_sc, npts, pl, offsets, cursor, (uint32_t*)d_sorted);
     CUDA_TRY(ctx, cudaMemsetAsync(buckets, 0, sizeof(jac_pt) * (size_t)pl.K * pl.B, st));   // Z = 0: identity
     cudaEventRecord(ctx->ev_k0, st);
@@ -755,7 +831,7 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(pl, buckets, chunk_out);
     k_msm_window_fold<<<pl.K, FOLD_THREADS, 0, st>>>(pl, chunk_out, windows);
     k_msm_horner<<<1, 32, 0, st>>>(pl, windows, lin_total, bad, (uint64_t*)partial192);
-    ctx->launches += 13;
+    ctx->launches += 14;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
 }
@@ -784,7 +860,30 @@ int schnorr_b200_batch_finish_dev(schnorr_b200_ctx* ctx, size_t n_partials, cons
     if (!ctx || !partials192 || !result216 || n_partials == 0) return SCHNORR_B200_EARG;
     NOT_ON_MULTI(ctx);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    k_batch_finish<<<1, 32, 0, ctx->stream>>>(n_partials, (const uint64_t*)partials192, ctx->gtab, result216);
+    k_batch_finish<<<1, 32, 0, ctx->stream>>>(n_partials, (const uint64_t*)partials192, ctx->gtab, result216, nullptr);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+// whole single-device batch on device buffers: partial MSM with (sum s e) G computed beside it, then the finish
+int schnorr_b200_verify_batch_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                                  const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                                  const uint8_t* rand32, uint8_t* result216) {
+    if (!ctx || !result216 || (n && (!sigs81 || !pk96 || !msg_off || !rand32))) return SCHNORR_B200_EARG;
+    NOT_ON_MULTI(ctx);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* d_res;
+    if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192 + 128, &d_res)) return rc;
+    uint8_t* partial = (uint8_t*)d_res + 64 + RESULT_BYTES;
+    uint64_t* rhs_pre = n ? (uint64_t*)(partial + 192) : nullptr;
+    if (n == 0) {
+        if (int rc = schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial)) return rc;
+    } else {
+        if (int rc = batch_partial_impl(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, partial, rhs_pre)) return rc;
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
+    }
+    k_batch_finish<<<1, 32, 0, ctx->stream>>>(1, (const uint64_t*)partial, ctx->gtab, result216, rhs_pre);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return SCHNORR_B200_OK;
@@ -816,7 +915,7 @@ int schnorr_b200_batch_finish(schnorr_b200_ctx* ctx, size_t n_partials, const ui
 // host inputs -> staged on the device -> one 192-byte partial at `partial` (device memory of this context)
 static int batch_partial_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
                               const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
-                              uint8_t* partial) {
+                              uint8_t* partial, uint64_t* rhs_pre = nullptr) {
     if (n == 0) return schnorr_b200_batch_partial_dev(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, partial);
     CHECK_MSG_OFF(ctx, n, msg_off);
     size_t mb = msg_off[n];
@@ -843,7 +942,7 @@ static int batch_partial_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     CUDA_TRY(ctx, cudaMemcpyAsync(d_rand, rand32, n * 32, cudaMemcpyHostToDevice, st));
     if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync(d_inf, pk_inf, n, cudaMemcpyHostToDevice, st));
     return batch_partial_impl(ctx, n, (uint8_t*)d_sig, (uint8_t*)d_pk, (uint8_t*)d_inf, (uint8_t*)d_m, (uint64_t*)d_off,
-                              (uint8_t*)d_rand, partial);
+                              (uint8_t*)d_rand, partial, rhs_pre);
 }
 
 static int multi_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
@@ -857,11 +956,15 @@ int schnorr_b200_verify_batch(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     if (!ctx->shards.empty()) return multi_verify_batch(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, verdict, lhs97, rhs97);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     void* d_res;
-    if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192, &d_res)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_L, 64 + RESULT_BYTES + 192 + 128, &d_res)) return rc;
     uint8_t* res = (uint8_t*)d_res + 64;
     uint8_t* partial = res + RESULT_BYTES;
-    if (int rc = batch_partial_host(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, partial)) return rc;
-    if (int rc = schnorr_b200_batch_finish_dev(ctx, 1, partial, res)) return rc;
+    uint64_t* rhs_pre = n ? (uint64_t*)(partial + 192) : nullptr;   // (sum s e) G computed beside the MSM
+    if (int rc = batch_partial_host(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, rand32, partial, rhs_pre)) return rc;
+    if (rhs_pre) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));
+    k_batch_finish<<<1, 32, 0, ctx->stream>>>(1, (const uint64_t*)partial, ctx->gtab, res, rhs_pre);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
     return read_result(ctx, res, verdict, lhs97, rhs97);
 }
 

@@ -296,6 +296,11 @@ class Engine:
         self._check(self._L.schnorr_b200_sign_many_dev(self._h, n, _ptr(sk32), _ptr(pk96), _ptr(pk_inf), _ptr(msgs),
                                                        _ptr(off), _ptr(nonce32), _ptr(sigs81)), "sign_many_dev")
 
+    def verify_batch_dev(self, n, sigs81, pk96, pk_inf, msgs, off, rand32, result216):
+        """Whole single-device batch on device buffers; result216 (device) = verdict | lhs97 | rhs97 (see the header)."""
+        self._check(self._L.schnorr_b200_verify_batch_dev(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(pk_inf), _ptr(msgs),
+                                                          _ptr(off), _ptr(rand32), _ptr(result216)), "verify_batch_dev")
+
     def batch_partial_dev(self, n, sigs81, pk96, pk_inf, msgs, off, rand32, partial192):
         self._check(self._L.schnorr_b200_batch_partial_dev(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(pk_inf),
                                                            _ptr(msgs), _ptr(off), _ptr(rand32), _ptr(partial192)),
