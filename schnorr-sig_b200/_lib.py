@@ -33,6 +33,8 @@ _SIGNATURES = {
     "schnorr_b200_verify_keyed_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
     "schnorr_b200_verify_batch": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 6 + [C.POINTER(C.c_int), _u8p, _u8p]),
     "schnorr_b200_verify_batch_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
+    "schnorr_b200_locate_invalid": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7 + [C.POINTER(C.c_uint64)]),
+    "schnorr_b200_locate_invalid_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
     "schnorr_b200_batch_partial_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
     "schnorr_b200_batch_finish_dev": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p]),
     "schnorr_b200_batch_finish": (C.c_int, [C.c_void_p, _sz, _u8p, C.POINTER(C.c_int), _u8p, _u8p]),

@@ -276,26 +276,32 @@ def verify_batch(signatures, public_keys, messages, rng=None) -> Result:
     return verify_prepared_batch(rand, signatures, public_keys, messages)
 
 
-def locate_invalid(signatures, public_keys, messages):
-    """Failed-batch localisation (the reference returns one Err for the whole batch,
-    src/batch.rs:125-129): re-checks the items one by one on the GPU (the independent-verification kernel)
-    and returns [(index, SignatureError), ...].  Note the single-verification semantics apply here:
-    an off-subgroup key is reported as InvalidPublicKey although verify_batch itself does not test it."""
+def locate_invalid(signatures, public_keys, messages, rng=None):
+    """Failed-batch localisation.  The reference returns one Err for the whole batch
+    (src/batch.rs:125-129); this returns [(index, SignatureError), ...] for every item whose own term of the batch
+    equation fails -- BATCH semantics (src/batch.rs:102-106): the signature's point is decompressed with its flag byte,
+    public keys are not subgroup-checked.  A signature with a flipped y-sign flag is therefore reported here (it makes
+    verify_batch fail) although Signature::verify accepts it.  Runs on the device: bisection over partial MSMs, then an
+    exact per-item check of the failing slices (schnorr_b200_locate_invalid).  Malformed encodings panic as in
+    verify_batch."""
     n = len(signatures)
     assert len(public_keys) == n and len(messages) == n
     if n == 0:
         return []
+    rng = rng or OsRng()
     sigs = np.frombuffer(b"".join(s.to_bytes() for s in signatures), dtype=np.uint8).reshape(n, 81)
     pks = np.frombuffer(b"".join(k.xy for k in public_keys), dtype=np.uint8).reshape(n, 96)
     inf = np.array([k.infinity for k in public_keys], dtype=np.uint8)
     blob, off = _pack(messages)
-    v = default_engine().verify_many(sigs, pks, inf, blob, off)
+    rand = np.zeros((n, 32), dtype=np.uint8)
+    for i in range(n):
+        rand[i] = np.frombuffer(_random_scalar(rng).to_bytes(32, "little"), dtype=np.uint8)
+    flags = default_engine().locate_invalid(sigs, pks, inf, blob, off, rand)
     out = []
-    for i in np.nonzero(v)[0]:
-        if v[i] == MALFORMED:
-            raise PanicError("signature %d has a non-canonical encoding" % i)
-        out.append((int(i), SignatureError(SignatureError.InvalidPublicKey if v[i] == INVALID_PUBLIC_KEY
-                                           else SignatureError.InvalidSignature)))
+    for i in np.nonzero(flags)[0]:
+        if flags[i] == MALFORMED:
+            raise PanicError("signature %d has a non-canonical or undecodable encoding" % i)
+        out.append((int(i), SignatureError(SignatureError.InvalidSignature)))
     return out
 
 

@@ -735,6 +735,53 @@ __global__ void __launch_bounds__(32) k_batch_finish(size_t np, const uint64_t* 
     result[112 + 96] = rinf ? 1 : 0;
 }
 
+// ---- f3: failed-batch localisation --------------------------------------------------------------
+// The reference returns ONE Err for the whole batch (src/batch.rs:125-129).  What the batch equation sums per item is
+//     D_i = R_i - h_i P_i - e_i G          with R_i = from_compressed(sig_i.x) INCLUDING its flag byte (src/batch.rs:104)
+// and no subgroup check on P_i (src/batch.rs:102-106) -- so "item i is what makes the batch fail" means D_i != O, which is
+// NOT the verdict of Signature::verify (x-only comparison, flag byte ignored, subgroup check first).  k_batch_item_check
+// evaluates exactly that for the items of a work list (exact Jacobian arithmetic: adversarial inputs welcome):
+//     out[i] = 0  D_i == O      2  D_i != O      3  malformed (the reference panics: src/batch.rs:67,104)
+__global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_batch_item_check(
+    soa_batch in, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off, const uint64_t* __restrict__ gtab,
+    uint8_t* __restrict__ out) {
+    struct d_slot {
+        jac_pt p;
+        uint64_t pad;
+    };
+    __shared__ d_slot s_d[VERIFY_THREADS];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    uint8_t fl = in.flags[i];
+    fp6 sx = load_fp6_planes(in.planes, 0, in.n, i);
+    scalar e = load_scalar_planes(in.planes, 3, in.n, i);
+    fp6 px = load_fp6_planes(in.planes, 5, in.n, i);
+    fp6 py = load_fp6_planes(in.planes, 8, in.n, i);
+    bool pk_inf = fl & FL_PK_INF;
+    fp6 rx, ry;
+    bool r_inf = true;
+    bool ok = !(fl & (FL_MALFORMED | FL_X_BAD)) && decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);
+    if (!ok) {
+        out[i] = VERDICT_MALFORMED;
+        return;
+    }
+    uint64_t off = msg_off[i];
+    scalar h = challenge_scalar(sx, px, py, pk_inf, msgs + off, msg_off[i + 1] - off);
+    jac_pt r;
+    (void)torsion_check_and_mul(jac_from_affine(px, py, pk_inf), h, &r, &s_d[threadIdx.x].p);   // h P (subgroup verdict unused)
+    fixed_base_accumulate(&r, e, gtab);                                                          // + e G
+    bool same;
+    if (jac_is_identity(r)) {
+        same = r_inf;
+    } else if (r_inf) {
+        same = false;
+    } else {  // (X, Y, Z) == (x, y):  X == x Z^2  and  Y == y Z^3
+        fp6 zz = fp6_sqr(r.Z);
+        same = fp6_eq(r.X, fp6_mul(rx, zz)) && fp6_eq(r.Y, fp6_mul(ry, fp6_mul(zz, r.Z)));
+    }
+    out[i] = same ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
+}
+
 // ---- host orchestration ----------------------------------------------------------------------
 // rhs_pre (optional, device, 13 x u64): single-device batches get (sum s_i e_i) G computed on the second stream beside the
 // MSM; the caller's finish kernel must wait on ctx->ev_aux
@@ -886,6 +933,132 @@ int schnorr_b200_verify_batch_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t
     k_batch_finish<<<1, 32, 0, ctx->stream>>>(1, (const uint64_t*)partial, ctx->gtab, result216, rhs_pre);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
+    return SCHNORR_B200_OK;
+}
+
+// Bisection over partial MSMs on DEVICE buffers.  A range whose own random linear combination
+//     sum_{i in range} s_i R_i - s_i h_i P_i  ==  (sum_{i in range} s_i e_i) G
+// holds is clean (up to the 2^-255 soundness error of the batch itself); a failing range is cut into LOCATE_FANOUT
+// sub-ranges, each checked by its own partial MSM; ranges of at most LOCATE_LEAF signatures -- or everything that is left
+// once the suspects stop shrinking -- go through k_batch_item_check.  One bad signature among 2^20 costs about two batch
+// verifications; a batch riddled with bad signatures degrades to one per-item pass.
+static constexpr size_t LOCATE_LEAF = 4096;
+static constexpr int LOCATE_FANOUT = 8;
+struct locate_range {
+    size_t lo, hi;
+};
+static int locate_items(schnorr_b200_ctx* ctx, const std::vector<locate_range>& ranges, const uint8_t* sigs81,
+                        const uint8_t* pk96, const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                        uint8_t* flags) {
+    for (const locate_range& r : ranges) {
+        size_t cn = r.hi - r.lo;
+        if (cn == 0) continue;
+        soa_batch soa;
+        if (int rc = alloc_soa(ctx, cn, &soa)) return rc;
+        k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, ctx->stream>>>(cn, sigs81 + 81 * r.lo, pk96 + 96 * r.lo,
+                                                                                   pk_inf ? pk_inf + r.lo : nullptr, soa);
+        k_batch_item_check<<<grid_for(cn, VERIFY_THREADS), VERIFY_THREADS, 0, ctx->stream>>>(soa, msgs, msg_off + r.lo, ctx->gtab,
+                                                                                           flags + r.lo);
+        ctx->launches += 2;
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // the SoA scratch is reused by the next range
+    }
+    return SCHNORR_B200_OK;
+}
+
+int schnorr_b200_locate_invalid_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                                    const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off,
+                                    const uint8_t* rand32, uint8_t* flags) {
+    if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !rand32 || !flags))) return SCHNORR_B200_EARG;
+    NOT_ON_MULTI(ctx);
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemsetAsync(flags, 0, n, ctx->stream));
+    std::vector<locate_range> suspects{{0, n}}, leaves;
+    void* d_res;
+    const size_t slot = RESULT_BYTES + 192 + 40;   // result | partial, per sub-range
+    if (int rc = ensure_scratch(ctx, SL_L, 64 + slot * LOCATE_FANOUT * 64, &d_res)) return rc;
+    uint8_t* base = (uint8_t*)d_res + 64;
+    bool first = true;
+    while (!suspects.empty()) {
+        // cut every suspect range (the whole batch is first checked as it is: a batch that verifies has no culprit)
+        std::vector<locate_range> parts;
+        for (const locate_range& r : suspects) {
+            size_t len = r.hi - r.lo;
+            if (len <= LOCATE_LEAF) {
+                leaves.push_back(r);
+                continue;
+            }
+            int f = first ? 1 : LOCATE_FANOUT;
+            size_t step = (len + f - 1) / f;
+            for (size_t lo = r.lo; lo < r.hi; lo += step) parts.push_back({lo, lo + step < r.hi ? lo + step : r.hi});
+        }
+        first = false;
+        suspects.clear();
+        // too many pieces: the batch is riddled with bad signatures, finish item by item
+        if (parts.size() > (size_t)LOCATE_FANOUT * 64) {
+            for (const locate_range& r : parts) leaves.push_back(r);
+            break;
+        }
+        std::vector<uint8_t> host(parts.size() * slot);
+        for (size_t k = 0; k < parts.size(); k++) {
+            const locate_range& r = parts[k];
+            uint8_t* res = base + k * slot;
+            uint8_t* partial = res + RESULT_BYTES;
+            if (int rc = batch_partial_impl(ctx, r.hi - r.lo, sigs81 + 81 * r.lo, pk96 + 96 * r.lo, pk_inf ? pk_inf + r.lo : nullptr,
+                                            msgs, msg_off + r.lo, rand32 + 32 * r.lo, partial))
+                return rc;
+            k_batch_finish<<<1, 32, 0, ctx->stream>>>(1, (const uint64_t*)partial, ctx->gtab, res, nullptr);
+            ctx->launches += 1;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), base, parts.size() * slot, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t k = 0; k < parts.size(); k++)
+            if (host[k * slot] != VERDICT_OK) suspects.push_back(parts[k]);   // Err or malformed: look inside
+    }
+    return locate_items(ctx, leaves, sigs81, pk96, pk_inf, msgs, msg_off, flags);
+}
+
+int schnorr_b200_locate_invalid(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                                const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* rand32,
+                                uint8_t* flags, uint64_t* n_bad) {
+    if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !rand32 || !flags))) return SCHNORR_B200_EARG;
+    if (n_bad) *n_bad = 0;
+    if (n == 0) return SCHNORR_B200_OK;
+    schnorr_b200_ctx* c = ctx->shards.empty() ? ctx : ctx->shards[0];   // localisation runs on the first device
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CHECK_MSG_OFF(ctx, n, msg_off);
+    size_t mb = msg_off[n];
+    if (mb && !msgs) return SCHNORR_B200_EARG;
+    // dedicated staging (slot M is only used by verify_many's work lists): inputs stay resident across the bisection
+    size_t sz_sig = (n * 81 + 255) & ~(size_t)255, sz_pk = (n * 96 + 255) & ~(size_t)255, sz_m = (mb + 255) & ~(size_t)255,
+           sz_off = ((n + 1) * 8 + 255) & ~(size_t)255, sz_rand = (n * 32 + 255) & ~(size_t)255, sz_inf = (n + 255) & ~(size_t)255;
+    void* blob;
+    if (int rc = ensure_scratch(c, SL_M, sz_sig + sz_pk + sz_m + sz_off + sz_rand + 2 * sz_inf, &blob)) return rc;
+    uint8_t* p = (uint8_t*)blob;
+    uint8_t *d_sig = p; p += sz_sig;
+    uint8_t *d_pk = p; p += sz_pk;
+    uint8_t *d_m = p; p += sz_m;
+    uint8_t *d_off = p; p += sz_off;
+    uint8_t *d_rand = p; p += sz_rand;
+    uint8_t *d_inf = p; p += sz_inf;
+    uint8_t *d_flags = p;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaMemcpyAsync(d_sig, sigs81, n * 81, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(d_pk, pk96, n * 96, cudaMemcpyHostToDevice, st));
+    if (mb) CUDA_TRY(c, cudaMemcpyAsync(d_m, msgs, mb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(d_off, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(d_rand, rand32, n * 32, cudaMemcpyHostToDevice, st));
+    if (pk_inf) CUDA_TRY(c, cudaMemcpyAsync(d_inf, pk_inf, n, cudaMemcpyHostToDevice, st));
+    int rc = schnorr_b200_locate_invalid_dev(c, n, d_sig, d_pk, pk_inf ? d_inf : nullptr, d_m, (const uint64_t*)d_off, d_rand, d_flags);
+    if (rc) {
+        if (c != ctx) ctx->err = c->err;
+        return rc;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(flags, d_flags, n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    if (n_bad)
+        for (size_t i = 0; i < n; i++) *n_bad += flags[i] != 0;
     return SCHNORR_B200_OK;
 }
 

@@ -186,6 +186,22 @@ class Engine:
                     "verify_batch")
         return verdict.value, lhs, rhs
 
+    def locate_invalid(self, sigs81, pk96, pk_inf, msgs, off, rand32):
+        """Failed-batch localisation in batch semantics -> uint8[n]: 0 clean, 2 bad, 3 malformed (see the header)."""
+        sigs81, pk96, msgs, rand32 = _u8(sigs81, 81), _u8(pk96, 96), _u8(msgs), _u8(rand32, 32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = sigs81.shape[0]
+        self._check_offsets(n, pk96.shape[0], off, msgs)
+        if rand32.shape[0] != n:
+            raise AssertionError("one randomiser per signature")
+        inf = None if pk_inf is None else _u8(pk_inf)
+        self._check_inf(n, inf)
+        flags = np.zeros(n, dtype=np.uint8)
+        nb = C.c_uint64(0)
+        self._check(self._L.schnorr_b200_locate_invalid(self._h, n, _ptr(sigs81), _ptr(pk96), _ptr(inf), _ptr(msgs), _ptr(off),
+                                                        _ptr(rand32), _ptr(flags), C.byref(nb)), "locate_invalid")
+        return flags
+
     def batch_partial(self, sigs81, pk96, pk_inf, msgs, off, rand32):
         """This rank's share of a batch: host arrays in, the 192-byte partial out (multi-GPU form).
         torch is used only to hold the device buffers."""
