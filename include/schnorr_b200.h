@@ -47,6 +47,15 @@ extern "C" {
 
 typedef struct schnorr_b200_ctx schnorr_b200_ctx;
 
+/* Value-level provenance of the curve / hash constants compiled into the library (include/cheetah_params.h).
+ * 0 = NOT pinned to the upstream `cheetah` / `hash` crates: the reference's tests hold no generator, digest or signature
+ * known answers and its dependencies are un-vendored git crates, so the generator is a placeholder and the Rescue
+ * instance is recalled / spec-derived; every result is bit-exact against the restated oracle (oracle/), and keys /
+ * signatures interoperate with the real crate only after rust/dump_params has been run on a machine with cargo and the
+ * header regenerated.  schnorr_b200_create prints this once per process while it is 0. */
+int schnorr_b200_params_pinned(void);
+const char *schnorr_b200_params_provenance(void);
+
 /* Creates a context on CUDA device `device`: stream, scratch arena and the fixed-base table of G
  * (the reference's `cheetah::BASEPOINT_TABLE`, src/signature.rs:19) built on the device. */
 int schnorr_b200_create(int device, schnorr_b200_ctx **out);

@@ -359,13 +359,39 @@ def decompress(b):
 
 
 # ----------------------------------------------------------------------------- parameters
+def upstream_dump():
+    """params/upstream_dump.json = output of rust/dump_params run against the REAL cheetah / hash crates (absent on this
+    box: no cargo, no network).  When it exists the generator comes from it and tests/test_oracle_pins.py checks every
+    dumped known answer; until then the oracle is "parity unpinned" at value level."""
+    global _DUMP
+    try:
+        return _DUMP
+    except NameError:
+        import json
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "params", "upstream_dump.json")
+        _DUMP = json.load(open(path)) if os.path.exists(path) else None
+        return _DUMP
+
+
+def _limbs_from_hex(h):
+    b = bytes.fromhex(h)
+    return tuple(int.from_bytes(b[8 * i:8 * i + 8], "little") for i in range(6))
+
+
 def generator():
-    """PLACEHOLDER generator: G := [cofactor] * KAT point; order q."""
+    """The generator of the prime-order subgroup.  Upstream value when params/upstream_dump.json exists; otherwise the
+    PLACEHOLDER G := [cofactor] * KAT point, reproducible from reference data alone and of order q."""
     global _G
     try:
         return _G
     except NameError:
-        _G = pt_mul((KAT_X, KAT_Y), COFACTOR)
+        d = upstream_dump()
+        if d is not None:
+            _G = (_limbs_from_hex(d["generator"]["x"]), _limbs_from_hex(d["generator"]["y"]))
+            assert on_curve(_G) and pt_mul(_G, Q) is INF
+        else:
+            _G = pt_mul((KAT_X, KAT_Y), COFACTOR)
         return _G
 
 

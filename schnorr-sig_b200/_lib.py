@@ -12,6 +12,8 @@ _sz = C.c_size_t
 
 _SIGNATURES = {
     "schnorr_b200_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "schnorr_b200_params_pinned": (C.c_int, []),
+    "schnorr_b200_params_provenance": (C.c_char_p, []),
     "schnorr_b200_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "schnorr_b200_device_count": (C.c_int, [C.c_void_p]),
     "schnorr_b200_destroy": (None, [C.c_void_p]),

@@ -14,7 +14,11 @@
 namespace sb {
 
 // circulant first row (RESCUE_MDS_ROW) and round constants (RESCUE_ARK) of cheetah_params.h
-SB_CONSTANT uint32_t c_mds_row[12] = {7, 23, 8, 26, 13, 10, 9, 7, 6, 22, 21, 8};
+SB_CONSTANT uint32_t c_mds_row[12] = RESCUE_MDS_ROW_INIT;
+// rescue_mds_ark below sums twelve (32-bit half) x (matrix entry) products in one 64-bit register without carries and
+// indexes the first row cyclically: both properties are checked where the parameters are generated and again here
+static_assert(RESCUE_MDS_IS_CIRCULANT == 1, "rescue_mds_ark needs a circulant MDS matrix");
+static_assert(RESCUE_MDS_MAX_ENTRY < (1u << 28), "MDS entries too large for the carry-free accumulation of rescue_mds_ark");
 #if defined(__CUDACC__)
 __constant__ uint64_t c_ark[2 * RESCUE_ROUNDS * 12];  // filled from RESCUE_ARK at context creation
 #define SB_ARK(i) c_ark[i]
@@ -31,8 +35,8 @@ SB_DEV fp_t rescue_sbox(fp_t x) {
     return fp_mul_nc(x3, x4);
 }
 
-// y = M * s + k  with M circulant, entries <= 26: the low and high 32-bit halves of the inputs are
-// accumulated separately in 64-bit registers (12 * 26 * 2^32 < 2^41: no carries), one reduction per output.
+// y = M * s + k  with M circulant, entries < 2^28 (26 for the shipped parameters): the low and high 32-bit halves of the
+// inputs are accumulated separately in 64-bit registers (12 * 2^28 * 2^32 < 2^64: no carries), one reduction per output.
 SB_DEV void rescue_mds_ark(fp_t* s, int ark_row) {
     fp_t t[12];
 #pragma unroll

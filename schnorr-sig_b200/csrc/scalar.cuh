@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/cheetah_params.h"
 #include "fp.cuh"
 
 namespace sb {
@@ -18,14 +19,12 @@ struct scalar {
 #else
 #define SB_CONSTANT static const
 #endif
-// q and 2^512 mod q, little-endian 32-bit limbs (include/cheetah_params.h: CHEETAH_Q32, SCALAR_R2_32)
-SB_CONSTANT uint32_t c_q32[8] = {0xaed4accfu, 0xd443623eu, 0x30157722u, 0x327aa723u,
-                                 0x990a37b5u, 0x563fbf0fu, 0x3b3f22d0u, 0x7af2599bu};
-SB_CONSTANT uint32_t c_r2_32[8] = {0x2a974d84u, 0x5a93b156u, 0x9f39eecdu, 0x5a531464u,
-                                   0xa30fdfc6u, 0xa2780be8u, 0xfd96d1bbu, 0x2a68a265u};
+// q, 2^512 mod q and -q^-1 mod 2^32 come from the generated parameter header (tools/gen_params.py): no literal copy here
+SB_CONSTANT uint32_t c_q32[8] = CHEETAH_Q32_INIT;
+SB_CONSTANT uint32_t c_r2_32[8] = SCALAR_R2_32_INIT;
 #define SB_CONST_Q(i) c_q32[i]
 #define SB_CONST_R2(i) c_r2_32[i]
-static constexpr uint32_t SC_QINV32 = 0xdd8b25d1u;  // -q^-1 mod 2^32 (include/cheetah_params.h)
+static constexpr uint32_t SC_QINV32 = SCALAR_QINV32;
 
 SB_DEV scalar sc_zero() { return scalar{{0, 0, 0, 0, 0, 0, 0, 0}}; }
 SB_DEV bool sc_is_zero(const scalar& a) {

@@ -702,9 +702,24 @@ static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint
 
 extern "C" {
 
+int schnorr_b200_params_pinned(void) { return CHEETAH_PARAMS_PINNED; }
+const char* schnorr_b200_params_provenance(void) { return CHEETAH_PARAMS_PROVENANCE; }
+
 int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     if (!out) return SCHNORR_B200_EARG;
     *out = nullptr;
+#if !CHEETAH_PARAMS_PINNED
+    {   // once per process: results are bit-exact against the RESTATED oracle only
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "schnorr_b200: curve / hash parameters are NOT pinned to the upstream cheetah / hash crates (%s). "
+                            "Keys and signatures interoperate with the real schnorr-sig crate only after "
+                            "rust/dump_params has been run and include/cheetah_params.h regenerated.\n",
+                    CHEETAH_PARAMS_PROVENANCE);
+        }
+    }
+#endif
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
         (void)cudaGetLastError();

@@ -87,7 +87,8 @@ def main():
         "kat_point": {"x": [hex(c) for c in o.KAT_X], "y": [hex(c) for c in o.KAT_Y],
                       "tag": "REF src/signature.rs:387-404"},
         "generator": {"x": [hex(c) for c in G[0]], "y": [hex(c) for c in G[1]],
-                      "tag": "PLACEHOLDER = [cofactor]*kat_point; true cheetah generator unknown"},
+                      "tag": ("REF (dumped from the cheetah crate: params/upstream_dump.json)" if o.upstream_dump() is not None
+                              else "PLACEHOLDER = [cofactor]*kat_point; true cheetah generator unknown")},
         "compressed_flags": {"infinity_bit": 7, "sign_bit": 6,
                              "tag": "bit 7 REF src/public.rs:95-101; bit 6 + lexicographic rule RECALLED"},
         "rescue": {
@@ -128,6 +129,12 @@ def main():
              " * Constants of the Cheetah curve / Rescue hash shared by the CPU oracle (oracle/cref.c)\n"
              " * and the CUDA engine (schnorr-sig_b200/csrc).  Plain C, usable from C, C++ and CUDA. */\n"
              "#ifndef CHEETAH_PARAMS_H\n#define CHEETAH_PARAMS_H\n#include <stdint.h>\n\n")
+    # value-level provenance: 1 only once EVERY constant below carries a REF / VERIFIED tag (i.e. was dumped from the
+    # real cheetah / hash crates, rust/dump_params); the library reports it (schnorr_b200_params_pinned)
+    h.append("#define CHEETAH_PARAMS_PINNED 0\n")
+    h.append("#define CHEETAH_PARAMS_PROVENANCE \"generator: PLACEHOLDER ([cofactor] * KAT point of src/signature.rs:387-404); "
+             "Rescue rounds / MDS / padding: RECALLED; round constants: SPEC-DERIVED (ePrint 2020/1143); y-sign flag bit: "
+             "RECALLED; p, Fp6, curve, q, KAT point, encodings: REF / VERIFIED\"\n")
     h.append("#define CHEETAH_P 0xffffffff00000001ULL            /* REF README.md:4 */\n")
     h.append("#define CHEETAH_CURVE_B0 395ULL                    /* B = u + 395, REF README.md:4-5 */\n")
     h.append("#define CHEETAH_CURVE_B1 1ULL\n")
@@ -141,7 +148,8 @@ def main():
     h.append(arr32("CHEETAH_Q32", limbs32(Q, 8)))
     h.append("/* 2^512 mod q (Montgomery R^2, R = 2^256) */\n")
     h.append(arr32("SCALAR_R2_32", limbs32(r2, 8)))
-    h.append("/* generator [PLACEHOLDER = cofactor * KAT point] */\n")
+    h.append("/* generator [%s] */\n" % ("REF: params/upstream_dump.json" if o.upstream_dump() is not None
+                                          else "PLACEHOLDER = cofactor * KAT point"))
     h.append(arr64("CHEETAH_GX", list(G[0])))
     h.append(arr64("CHEETAH_GY", list(G[1])))
     h.append("/* off-subgroup known-answer point, REF src/signature.rs:387-404 */\n")
@@ -154,6 +162,21 @@ def main():
     h.append(arr8("CHEETAH_Q_WNAF4", q_wnaf4))
     h.append("/* Frobenius: (u^i)^p = FP6_FROB[i] * u^i */\n")
     h.append(arr64("FP6_FROB", frob6))
+    # Brace initialisers for constants that the device code keeps in __constant__ memory / constexpr tables: the kernels
+    # take them from HERE, so swapping params means regenerating this header and nothing else.
+    def init_list(vals, fmt):
+        return "{" + ", ".join(fmt % v for v in vals) + "}"
+    h.append("/* initialiser lists of the same constants for __constant__ / constexpr tables of the device code */\n")
+    h.append("#define CHEETAH_Q32_INIT %s\n" % init_list(limbs32(Q, 8), "0x%08xu"))
+    h.append("#define SCALAR_R2_32_INIT %s\n" % init_list(limbs32(r2, 8), "0x%08xu"))
+    row = list(o.MDS_FIRST_ROW)
+    # the device MDS layer (csrc/rescue.cuh: rescue_mds_ark) needs a CIRCULANT matrix with entries below 2^28 (twelve
+    # 32-bit x entry products are summed in one 64-bit register without carries)
+    assert all(mds[i][j] == row[(j - i) % 12] for i in range(12) for j in range(12)), "MDS matrix is not circulant"
+    assert max(row) < (1 << 28), "MDS entries too large for the carry-free accumulation of rescue_mds_ark"
+    h.append("#define RESCUE_MDS_ROW_INIT %s\n" % init_list(row, "%du"))
+    h.append("#define RESCUE_MDS_MAX_ENTRY %du\n" % max(row))
+    h.append("#define RESCUE_MDS_IS_CIRCULANT 1\n\n")
     h.append("/* Rescue circulant MDS first row [RECALLED] and full matrix */\n")
     h.append(arr64("RESCUE_MDS_ROW", list(o.MDS_FIRST_ROW), 6))
     h.append(arr64("RESCUE_MDS", [c for row in mds for c in row], 6))
