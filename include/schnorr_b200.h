@@ -170,6 +170,22 @@ int schnorr_b200_sign_many_dev(schnorr_b200_ctx *ctx, size_t n, const uint8_t *s
                                const uint8_t *pk_inf, const uint8_t *msgs, const uint64_t *msg_off,
                                const uint8_t *nonce32, uint8_t *sigs81);
 
+/* Hierarchical deterministic key derivation (src/derivation.rs), n children per call, one child per thread:
+ *   master keys      ExtendedPrivateKey::generate_master_key(seed)                   :66-84
+ *                    seeds32: n x 32 B -> xsk64: n x (private key 32 B LE || chain code 32 B)
+ *   private children ExtendedPrivateKey::derive_private(i) of ONE parent, hardened (i >= 2^31) or normal by index
+ *                                                                                     :90-153
+ *   public children  ExtendedPublicKey::derive_normal_public(i) of ONE parent        :249-277
+ *                    xpk81 = PublicKey::to_bytes() 49 B || chain code 32 B (= ExtendedPublicKey::to_bytes, :280-286)
+ * indices: n little-endian u32 (the reference's `&[u8; 4]`).  ok[i] = 1 where the reference returns Some: non-zero child
+ * key / non-identity tweak point, and for public children a non-hardened index.  Records of children whose ok is 0 are
+ * what the formulas give and must not be used.  HMAC-SHA512 and the fixed-base multiplication run on the device. */
+int schnorr_b200_derive_master_keys(schnorr_b200_ctx *ctx, size_t n, const uint8_t *seeds32, uint8_t *xsk64, uint8_t *ok);
+int schnorr_b200_derive_private_children(schnorr_b200_ctx *ctx, size_t n, const uint8_t *parent_xsk64,
+                                         const uint32_t *indices, uint8_t *children_xsk64, uint8_t *ok);
+int schnorr_b200_derive_public_children(schnorr_b200_ctx *ctx, size_t n, const uint8_t *parent_xpk81,
+                                        const uint32_t *indices, uint8_t *children_xpk81, uint8_t *ok);
+
 /* PublicKey::from_bytes / AffinePoint::from_compressed for n 49-byte records  src/public.rs:54-56
  * ok[i] = 1 when the record decodes (CtOption is_some). */
 int schnorr_b200_decompress(schnorr_b200_ctx *ctx, size_t n, const uint8_t *in49, uint8_t *pk96, uint8_t *pk_inf,

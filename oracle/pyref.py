@@ -556,3 +556,39 @@ def prf(seed: int, domain: str, index: int, nbytes: int) -> bytes:
 def synth_scalar(seed, domain, index):
     k = int.from_bytes(prf(seed, domain, index, 64), "little") % Q
     return k if k else 1
+
+
+# ----------------------------------------------------------------------------- HD derivation (src/derivation.rs)
+def _hmac_sha512(key: bytes, data: bytes) -> bytes:
+    import hashlib
+    import hmac
+    return hmac.new(key, data, hashlib.sha512).digest()
+
+
+def hd_master_key(seed32: bytes):
+    """ExtendedPrivateKey::generate_master_key (src/derivation.rs:66-84) -> (sk, chain code, is_some)."""
+    I = _hmac_sha512(b"Cheetah - Master extended key seed", seed32)
+    sk = int.from_bytes(I[:32], "little") % Q          # Scalar::from_bytes_non_canonical [INFERRED: value mod q]
+    return sk, I[32:], sk != 0
+
+
+def hd_derive_private(sk: int, chain: bytes, index: int):
+    """ExtendedPrivateKey::derive_private (src/derivation.rs:90-153): hardened (index >= 2^31) children hash
+    0^17 || sk, normal children hash PublicKey(sk).to_bytes(); child = I_L + sk."""
+    i4 = index.to_bytes(4, "little")
+    if index >> 31:
+        data = bytes(17) + sk.to_bytes(32, "little") + i4
+    else:
+        data = bytes(compress(pt_mul(generator(), sk))) + i4
+    I = _hmac_sha512(chain, data)
+    child = (int.from_bytes(I[:32], "little") + sk) % Q
+    return child, I[32:], child != 0
+
+
+def hd_derive_public(pk, chain: bytes, index: int):
+    """ExtendedPublicKey::derive_normal_public (src/derivation.rs:249-277): child = I_L G + pk; None for a hardened
+    index or an identity tweak point."""
+    I = _hmac_sha512(chain, bytes(compress(pk)) + index.to_bytes(4, "little"))
+    t = int.from_bytes(I[:32], "little") % Q
+    point = pt_mul(generator(), t)
+    return pt_add(point, pk), I[32:], (point is not INF) and (index >> 31) == 0

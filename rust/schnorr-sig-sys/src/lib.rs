@@ -48,8 +48,12 @@ extern "C" {
         pk_inf: *mut u8, ok: *mut u8) -> c_int;
     pub fn schnorr_b200_compress(ctx: *mut schnorr_b200_ctx, n: usize, pk96: *const u8, pk_inf: *const u8,
         out49: *mut u8) -> c_int;
-    pub fn schnorr_b200_derive_children(ctx: *mut schnorr_b200_ctx, n: usize, parent: *const u8, indices: *const u32,
-        children: *mut u8, ok: *mut u8) -> c_int;
+    pub fn schnorr_b200_derive_master_keys(ctx: *mut schnorr_b200_ctx, n: usize, seeds32: *const u8, xsk64: *mut u8,
+        ok: *mut u8) -> c_int;
+    pub fn schnorr_b200_derive_private_children(ctx: *mut schnorr_b200_ctx, n: usize, parent_xsk64: *const u8,
+        indices: *const u32, children_xsk64: *mut u8, ok: *mut u8) -> c_int;
+    pub fn schnorr_b200_derive_public_children(ctx: *mut schnorr_b200_ctx, n: usize, parent_xpk81: *const u8,
+        indices: *const u32, children_xpk81: *mut u8, ok: *mut u8) -> c_int;
     pub fn schnorr_b200_set_dist_threshold(ctx: *mut schnorr_b200_ctx, max_signatures: usize) -> c_int;
     pub fn schnorr_b200_set_msm_geometry(ctx: *mut schnorr_b200_ctx, window_bits: c_int, segment_len: c_uint) -> c_int;
 }

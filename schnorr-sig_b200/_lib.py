@@ -44,6 +44,9 @@ _SIGNATURES = {
     "schnorr_b200_keygen_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
     "schnorr_b200_sign_many": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
     "schnorr_b200_sign_many_dev": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 7),
+    "schnorr_b200_derive_master_keys": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p]),
+    "schnorr_b200_derive_private_children": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p, _u8p]),
+    "schnorr_b200_derive_public_children": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p, _u8p]),
     "schnorr_b200_decompress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 4),
     "schnorr_b200_compress": (C.c_int, [C.c_void_p, _sz] + [_u8p] * 3),
     "schnorr_b200_debug_field_ops": (C.c_int, [C.c_void_p, _sz, _u8p, _u8p, _u8p]),

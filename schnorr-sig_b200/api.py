@@ -263,6 +263,122 @@ class KeyPair:
         return signature.verify(message, self.public_key)
 
 
+# ---- hierarchical deterministic derivation (src/derivation.rs) -----------------------------------------------------
+CHAIN_CODE_LENGTH = 32
+EXTENDED_PRIVATE_KEY_LENGTH = 64
+EXTENDED_PUBLIC_KEY_LENGTH = 81
+
+
+class ChainCode:
+    """BIP32-like chain code (src/derivation.rs:30-32)."""
+
+    def __init__(self, b: bytes):
+        b = bytes(b)
+        assert len(b) == CHAIN_CODE_LENGTH
+        self.bytes = b
+
+    def __eq__(self, other):
+        return isinstance(other, ChainCode) and self.bytes == other.bytes
+
+    def __hash__(self):
+        return hash(self.bytes)
+
+
+def _index_u32(i) -> int:
+    """The reference takes the index as `&[u8; 4]`, little-endian (src/derivation.rs:86-90); ints are accepted too."""
+    return int.from_bytes(bytes(i), "little") if isinstance(i, (bytes, bytearray, list, tuple)) else int(i)
+
+
+class ExtendedPrivateKey:
+    """A derivable private key and its chain code (src/derivation.rs:46-53).  Methods return None where the reference
+    returns a `CtOption` that is none."""
+
+    def __init__(self, key: PrivateKey, chaincode: ChainCode):
+        self.key, self.chaincode = key, chaincode
+
+    @classmethod
+    def generate_master_key(cls, seed: bytes):
+        seed = bytes(seed)
+        assert len(seed) == 32
+        out, ok = default_engine().derive_master_keys(np.frombuffer(seed, dtype=np.uint8).reshape(1, 32))
+        return cls._from_record(out[0]) if ok[0] else None
+
+    @classmethod
+    def _from_record(cls, rec):
+        rec = bytes(rec)
+        return cls(PrivateKey(int.from_bytes(rec[:32], "little")), ChainCode(rec[32:]))
+
+    def to_bytes(self) -> bytes:
+        return self.key.to_bytes() + self.chaincode.bytes
+
+    @classmethod
+    def from_bytes(cls, b: bytes):
+        b = bytes(b)
+        assert len(b) == EXTENDED_PRIVATE_KEY_LENGTH
+        key = PrivateKey.from_bytes(b[:32])
+        return None if key is None else cls(key, ChainCode(b[32:]))
+
+    def derive_private_many(self, indices):
+        """Children for many indices in one device call -> list of ExtendedPrivateKey / None."""
+        idx = np.array([_index_u32(i) for i in indices], dtype=np.uint32)
+        out, ok = default_engine().derive_private_children(self.to_bytes(), idx)
+        return [self._from_record(out[k]) if ok[k] else None for k in range(len(idx))]
+
+    def derive_private(self, i):
+        return self.derive_private_many([i])[0]
+
+    def derive_hardened_private(self, i):
+        return self.derive_private(i) if _index_u32(i) >> 31 else None          # src/derivation.rs:121-123
+
+    def derive_normal_private(self, i):
+        return None if _index_u32(i) >> 31 else self.derive_private(i)          # src/derivation.rs:149-151
+
+    def derive_public(self, i):
+        child = self.derive_private(i)
+        return None if child is None else ExtendedPublicKey.from_extended_private_key(child)
+
+    def __eq__(self, other):
+        return isinstance(other, ExtendedPrivateKey) and self.to_bytes() == other.to_bytes()
+
+
+class ExtendedPublicKey:
+    """A derivable public key and its chain code (src/derivation.rs:204-211)."""
+
+    def __init__(self, key: PublicKey, chaincode: ChainCode):
+        self.key, self.chaincode = key, chaincode
+
+    @classmethod
+    def from_extended_private_key(cls, xsk: ExtendedPrivateKey):
+        return cls(PublicKey.from_private(xsk.key), xsk.chaincode)
+
+    def to_bytes(self) -> bytes:
+        return self.key.to_bytes() + self.chaincode.bytes
+
+    @classmethod
+    def from_bytes(cls, b: bytes):
+        b = bytes(b)
+        assert len(b) == EXTENDED_PUBLIC_KEY_LENGTH
+        key = PublicKey.from_bytes(b[:49])
+        return None if key is None or key.infinity else cls(key, ChainCode(b[49:]))
+
+    def derive_normal_public_many(self, indices):
+        """Non-hardened public children for many indices in one device call (HMAC-SHA512 + one fixed-base
+        multiplication per child on the GPU) -> list of ExtendedPublicKey / None."""
+        idx = np.array([_index_u32(i) for i in indices], dtype=np.uint32)
+        out, ok = default_engine().derive_public_children(self.to_bytes(), idx)
+        res = []
+        for k in range(len(idx)):
+            key = PublicKey.from_bytes(bytes(out[k, :49])) if ok[k] else None
+            res.append(None if key is None else ExtendedPublicKey(key, ChainCode(bytes(out[k, 49:]))))
+        return res
+
+    def derive_normal_public(self, i):
+        return self.derive_normal_public_many([i])[0]
+
+    def __eq__(self, other):
+        return isinstance(other, ExtendedPublicKey) and (self.key, self.chaincode) == (other.key, other.chaincode)
+
+
 def verify_batch(signatures, public_keys, messages, rng=None) -> Result:
     """src/batch.rs:31-50: asserts equal lengths, draws one full-width random scalar per signature,
     checks  sum s_i R_i - sum s_i h_i P_i == (sum s_i e_i) G  on the GPU."""

@@ -22,6 +22,7 @@
 #include "verify.cuh"
 #include "dist.cuh"
 #include "debug_ops.cuh"
+#include "derive.cuh"
 
 using namespace sb;
 
@@ -512,6 +513,67 @@ __global__ void __launch_bounds__(128) k_split_keyed(size_t n, const uint8_t* __
 __global__ void k_mask_verdicts(size_t n, const uint8_t* __restrict__ ok, uint8_t* __restrict__ verdicts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && !ok[i]) verdicts[i] = VERDICT_MALFORMED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f4: hierarchical deterministic derivation (src/derivation.rs:66-277), one child per thread (derive.cuh)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_derive_master(size_t n, const uint8_t* __restrict__ seeds32, uint8_t* __restrict__ xsk64,
+                                                       uint8_t* __restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = derive_master(seeds32 + 32 * i, xsk64 + 64 * i) ? 1 : 0;
+}
+// parent49 = PublicKey::from(parent sk).to_bytes(), computed once by k_parent_public below
+__global__ void __launch_bounds__(128) k_derive_private(size_t n, const uint8_t* __restrict__ parent_xsk64,
+                                                        const uint8_t* __restrict__ parent49, const uint32_t* __restrict__ indices,
+                                                        uint8_t* __restrict__ children64, uint8_t* __restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = derive_private_child(parent_xsk64, parent49, indices[i], children64 + 64 * i) ? 1 : 0;
+}
+__global__ void k_parent_public(const uint8_t* __restrict__ parent_xsk64, const uint64_t* __restrict__ gtab, uint8_t* __restrict__ out49) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    scalar k = sc_from_u256(sc_load_le(parent_xsk64));
+    jac_pt P = fixed_base_mul(k, gtab);
+    fp6 x, y;
+    bool inf;
+    jac_to_affine(P, x, y, inf);
+    for (int c = 0; c < 6; c++)
+        for (int b = 0; b < 8; b++) out49[8 * c + b] = (uint8_t)((inf ? 0 : x.c[c]) >> (8 * b));
+    out49[48] = compress_flags(y, inf);
+}
+// children81 = 49-byte compressed child key || 32-byte chain code; parent96 / parent_inf = the decompressed parent key
+__global__ void __launch_bounds__(SIGN_THREADS) k_derive_public(size_t n, const uint8_t* __restrict__ parent_xpk81,
+                                                                const uint8_t* __restrict__ parent96,
+                                                                const uint8_t* __restrict__ parent_inf,
+                                                                const uint32_t* __restrict__ indices,
+                                                                const uint64_t* __restrict__ gtab, uint8_t* __restrict__ children81,
+                                                                uint8_t* __restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t index = indices[i];
+    uint8_t* o = children81 + 81 * i;
+    scalar t = derive_public_tweak(parent_xpk81, parent_xpk81 + 49, index, o + 49);
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(parent96);
+    fp6 px, py;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        px.c[k] = p[k];
+        py.c[k] = p[6 + k];
+    }
+    jac_pt acc = fixed_base_mul(t, gtab);                       // I_L G   (src/derivation.rs:263)
+    bool tweak_inf = jac_is_identity(acc);
+    acc = jac_madd(acc, px, py, parent_inf[0] != 0);            // + parent key (:264)
+    fp6 x, y;
+    bool inf;
+    jac_to_affine(acc, x, y, inf);
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) o[8 * k + b] = (uint8_t)((inf ? 0 : x.c[k]) >> (8 * b));
+    o[48] = compress_flags(y, inf);
+    ok[i] = (!tweak_inf && (index >> 31) == 0) ? 1 : 0;         // :270-275
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1164,6 +1226,82 @@ int schnorr_b200_sign_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sk32,
     CUDA_TRY(ctx, cudaMemsetAsync(d_nonce, 0, n * 32, ctx->stream));   // reusable staging arena
     CUDA_TRY(ctx, cudaMemcpyAsync(sigs81, d_out, n * 81, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+
+// ---- f4: hierarchical deterministic derivation ---------------------------------------------------------------
+int schnorr_b200_derive_master_keys(schnorr_b200_ctx* ctx, size_t n, const uint8_t* seeds32, uint8_t* xsk64, uint8_t* ok) {
+    if (!ctx || (n && (!seeds32 || !xsk64 || !ok))) return SCHNORR_B200_EARG;
+    MULTI_DISPATCH(ctx, schnorr_b200_derive_master_keys(ctx->shards[0], n, seeds32, xsk64, ok));
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_in, *d_out, *d_ok;
+    if (int rc = stage_in(ctx, SL_D, seeds32, n * 32, &d_in)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 64, &d_out)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_I, n, &d_ok)) return rc;
+    k_derive_master<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint8_t*)d_in, (uint8_t*)d_out, (uint8_t*)d_ok);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemsetAsync(d_in, 0, n * 32, ctx->stream));   // seeds are secrets
+    CUDA_TRY(ctx, cudaMemcpyAsync(xsk64, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, n * 64, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_derive_private_children(schnorr_b200_ctx* ctx, size_t n, const uint8_t* parent_xsk64, const uint32_t* indices,
+                                         uint8_t* children_xsk64, uint8_t* ok) {
+    if (!ctx || !parent_xsk64 || (n && (!indices || !children_xsk64 || !ok))) return SCHNORR_B200_EARG;
+    MULTI_DISPATCH(ctx, schnorr_b200_derive_private_children(ctx->shards[0], n, parent_xsk64, indices, children_xsk64, ok));
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_par, *d_idx, *d_out, *d_ok;
+    if (int rc = ensure_scratch(ctx, SL_D, 128, &d_par)) return rc;          // [0,64) parent, [64,128) its public key bytes
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_par, parent_xsk64, 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = stage_in(ctx, SL_F, indices, n * 4, &d_idx)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 64, &d_out)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_I, n, &d_ok)) return rc;
+    uint8_t* d_pk49 = (uint8_t*)d_par + 64;
+    k_parent_public<<<1, 32, 0, ctx->stream>>>((uint8_t*)d_par, ctx->gtab, d_pk49);
+    k_derive_private<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, (uint8_t*)d_par, d_pk49, (uint32_t*)d_idx, (uint8_t*)d_out,
+                                                               (uint8_t*)d_ok);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(children_xsk64, d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_par, 0, 128, ctx->stream));              // secrets do not stay in the arena
+    CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, n * 64, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_derive_public_children(schnorr_b200_ctx* ctx, size_t n, const uint8_t* parent_xpk81, const uint32_t* indices,
+                                        uint8_t* children_xpk81, uint8_t* ok) {
+    if (!ctx || !parent_xpk81 || (n && (!indices || !children_xpk81 || !ok))) return SCHNORR_B200_EARG;
+    MULTI_DISPATCH(ctx, schnorr_b200_derive_public_children(ctx->shards[0], n, parent_xpk81, indices, children_xpk81, ok));
+    if (n == 0) return SCHNORR_B200_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void *d_par, *d_idx, *d_out, *d_ok;
+    // parent record (81) | decompressed key (96) | identity flag (1) | decode flag (1), 16-byte aligned pieces
+    if (int rc = ensure_scratch(ctx, SL_D, 96 + 96 + 16 + 16, &d_par)) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_par, parent_xpk81, 81, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = stage_in(ctx, SL_F, indices, n * 4, &d_idx)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_E, n * 81, &d_out)) return rc;
+    if (int rc = ensure_scratch(ctx, SL_I, n, &d_ok)) return rc;
+    uint8_t *d_pk96 = (uint8_t*)d_par + 96, *d_inf = d_pk96 + 96, *d_dec = d_inf + 16;
+    k_decompress<<<1, 128, 0, ctx->stream>>>(1, (uint8_t*)d_par, d_pk96, d_inf, d_dec);   // ExtendedPublicKey::from_bytes (:295-311)
+    k_derive_public<<<grid_for(n, SIGN_THREADS), SIGN_THREADS, 0, ctx->stream>>>(n, (uint8_t*)d_par, d_pk96, d_inf, (uint32_t*)d_idx,
+                                                                                ctx->gtab, (uint8_t*)d_out, (uint8_t*)d_ok);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    uint8_t dec = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&dec, d_dec, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(children_xpk81, d_out, n * 81, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!dec) {  // the parent key does not decode: no child exists
+        ctx->err = "parent extended public key does not decode";
+        return SCHNORR_B200_EARG;
+    }
     return SCHNORR_B200_OK;
 }
 

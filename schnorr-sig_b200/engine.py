@@ -252,6 +252,34 @@ class Engine:
                                                    _ptr(nonce32), _ptr(out)), "sign_many")
         return out
 
+    # ---- hierarchical deterministic derivation (src/derivation.rs) -------------------------------------------------
+    def derive_master_keys(self, seeds32):
+        seeds32 = _u8(seeds32, 32)
+        n = seeds32.shape[0]
+        out, ok = np.zeros((n, 64), dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_derive_master_keys(self._h, n, _ptr(seeds32), _ptr(out), _ptr(ok)), "derive_master_keys")
+        return out, ok
+
+    def derive_private_children(self, parent_xsk64, indices):
+        parent = np.ascontiguousarray(np.frombuffer(bytes(parent_xsk64), dtype=np.uint8))
+        assert parent.size == 64
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        n = idx.shape[0]
+        out, ok = np.zeros((n, 64), dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_derive_private_children(self._h, n, _ptr(parent), _ptr(idx), _ptr(out), _ptr(ok)),
+                    "derive_private_children")
+        return out, ok
+
+    def derive_public_children(self, parent_xpk81, indices):
+        parent = np.ascontiguousarray(np.frombuffer(bytes(parent_xpk81), dtype=np.uint8))
+        assert parent.size == 81
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        n = idx.shape[0]
+        out, ok = np.zeros((n, 81), dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        self._check(self._L.schnorr_b200_derive_public_children(self._h, n, _ptr(parent), _ptr(idx), _ptr(out), _ptr(ok)),
+                    "derive_public_children")
+        return out, ok
+
     def decompress(self, in49):
         in49 = _u8(in49, 49)
         n = in49.shape[0]

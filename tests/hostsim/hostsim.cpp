@@ -11,6 +11,7 @@
 #include "../../include/cheetah_params.h"
 #include "../../schnorr-sig_b200/csrc/verify.cuh"
 #include "../../schnorr-sig_b200/csrc/debug_ops.cuh"
+#include "../../schnorr-sig_b200/csrc/derive.cuh"
 
 using namespace sb;
 
@@ -293,4 +294,18 @@ API void hs_jf_add_exact(const uint8_t* a96, int a_inf, uint64_t wa, const uint8
     jf_add_exact(&a, &b);
     *out_inf = a.w == 0;
     if (a.w != 0) jf_to_affine(a, out96);
+}
+
+// ---- HD derivation building blocks (derive.cuh) ----
+API void hs_hmac_sha512(const uint8_t* key, int key_len, const uint8_t* data, int data_len, uint8_t* out64) {
+    hmac_sha512_short(key, key_len, data, data_len, out64);
+}
+API void hs_sha512_short(const uint8_t* data, int len, uint8_t* out64) {
+    sha512_state s;
+    sha512_init(s);
+    sha512_finish_short(s, 0, data, len, out64);
+}
+API int hs_derive_master(const uint8_t* seed32, uint8_t* xsk64) { return derive_master(seed32, xsk64); }
+API int hs_derive_private_child(const uint8_t* xsk64, const uint8_t* pk49, uint32_t index, uint8_t* child64) {
+    return derive_private_child(xsk64, pk49, index, child64);
 }

@@ -463,3 +463,32 @@ def test_lazily_reduced_building_blocks_accept_non_canonical_operands(hostsim):
     for i in range(len(a)):
         hostsim.hs_debug_lazy_ops(p(a[i].copy()), p(b[i].copy()), p(out[i]))
     check_lazy_ops(a, b, out)
+
+
+def test_sha512_hmac_and_derivation_steps(hostsim):
+    """derive.cuh (f4): SHA-512 / HMAC-SHA512 against hashlib, master key and private children against the oracle's
+    restatement of src/derivation.rs:66-153."""
+    import hashlib
+    import hmac
+    rng = np.random.default_rng(71)
+    out = np.zeros(64, dtype=np.uint8)
+    for L in (0, 1, 55, 56, 64, 100, 111):
+        data = rng.integers(0, 256, max(L, 1), dtype=np.uint8)
+        hostsim.hs_sha512_short(p(data), L, p(out))
+        assert bytes(out) == hashlib.sha512(bytes(data[:L])).digest()
+    for kl, dl in ((32, 53), (34, 32), (1, 0), (128, 111), (64, 64)):
+        key = rng.integers(0, 256, kl, dtype=np.uint8)
+        data = rng.integers(0, 256, max(dl, 1), dtype=np.uint8)
+        hostsim.hs_hmac_sha512(p(key), kl, p(data), dl, p(out))
+        assert bytes(out) == hmac.new(bytes(key), bytes(data[:dl]), hashlib.sha512).digest()
+    seed = rng.integers(0, 256, 32, dtype=np.uint8)
+    x = np.zeros(64, dtype=np.uint8)
+    assert hostsim.hs_derive_master(p(seed), p(x)) == 1
+    sk, chain, ok = o.hd_master_key(bytes(seed))
+    assert ok and bytes(x) == sk.to_bytes(32, "little") + chain
+    pk49 = np.frombuffer(bytes(o.compress(o.pt_mul(o.generator(), sk))), dtype=np.uint8).copy()
+    child = np.zeros(64, dtype=np.uint8)
+    for index in (0, 1, 2**31 - 1, 2**31, 2**32 - 1, 123456789):
+        assert hostsim.hs_derive_private_child(p(x), p(pk49), C.c_uint32(index), p(child)) == 1
+        ck, cc, cok = o.hd_derive_private(sk, chain, index)
+        assert cok and bytes(child) == ck.to_bytes(32, "little") + cc
