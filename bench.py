@@ -602,7 +602,70 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
             small_calls["n%d_ms" % ns_] = float(np.mean(ts)) * 1e3
         small_calls["kernel"] = "k_verify_dist (one signature per six lanes)"
         out["small_calls"] = small_calls
+        out["criterion_protocol"] = criterion_protocol(eng, sb)
+        out["hash_sweep"] = hash_sweep(eng, torch, dev, stream, peak_w)
     return out
+
+
+def criterion_protocol(eng, sb):
+    """The reference's own Criterion cases (benches/schnorr.rs:22-24,67-96) through the host API, wall clock, mean of
+    20 samples (sample_size(20), benches/schnorr.rs:113): one Signature::verify for 8 / 80 / 160-byte messages and
+    verify_batch of 4 / 16 / 32 / 64 / 128 signatures over one shared 80-byte message."""
+    res = {"samples": 20, "verify_ms": {}, "verify_batch_ms": {}}
+    for L in (8, 80, 160):
+        w = sb.synth.signed_workload(eng, 0xC21 + L, 1, msg_len=L)
+        assert int(eng.verify_many(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"])[0]) == 0
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            eng.verify_many(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"])
+            ts.append(time.perf_counter() - t0)
+        res["verify_ms"]["%d_bytes" % L] = float(np.mean(ts)) * 1e3
+    for size in (4, 16, 32, 64, 128):
+        w = sb.synth.host_inputs(0xBA7 + size, size, 80)
+        w["blob"] = np.tile(w["blob"][:80], size)                 # one shared message (benches/schnorr.rs:81)
+        pk, inf = eng.keygen(w["sk"])
+        sigs = eng.sign_many(w["sk"], pk, inf, w["blob"], w["off"], w["nonce"])
+        assert eng.verify_batch(sigs, pk, inf, w["blob"], w["off"], w["rand"])[0] == 0
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            eng.verify_batch(sigs, pk, inf, w["blob"], w["off"], w["rand"])
+            ts.append(time.perf_counter() - t0)
+        res["verify_batch_ms"]["%d_signatures" % size] = float(np.mean(ts)) * 1e3
+    return res
+
+
+def hash_sweep(eng, torch, dev, stream, peak_w):
+    """BASELINE configs[1]: hash_message throughput for 2^10 ... 2^22 messages of 8 bytes on one GPU (device-resident
+    uniform field elements, CUDA events, second of two launches)."""
+    rng = np.random.default_rng(11)
+    nmax = 1 << 22
+    P = np.uint64(0xFFFFFFFF00000001)
+    def felts(k):
+        v = rng.integers(0, 2**64, k, dtype=np.uint64)
+        return np.where(v >= P, v - P, v).view(np.uint8)
+    with torch.cuda.stream(stream):
+        d_rx = torch.from_numpy(felts(6 * nmax).reshape(nmax, 48)).to(dev)
+        d_pk = torch.from_numpy(felts(12 * nmax).reshape(nmax, 96)).to(dev)
+        d_blob = torch.from_numpy(rng.integers(0, 256, nmax * 8, dtype=np.uint8)).to(dev)
+        d_off = torch.from_numpy((np.arange(nmax + 1, dtype=np.uint64) * np.uint64(8)).view(np.int64)).to(dev)
+        d_out = torch.empty((nmax, 32), dtype=torch.uint8, device=dev)
+        stream.synchronize()
+    rows = []
+    for lg in range(10, 23, 2):
+        n = 1 << lg
+        with torch.cuda.stream(stream):
+            eng.hash_messages_dev(n, d_rx, d_pk, d_blob, d_off, d_out)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            eng.hash_messages_dev(n, d_rx, d_pk, d_blob, d_off, d_out)
+            b.record(stream)
+            stream.synchronize()
+        ms = a.elapsed_time(b)
+        rows.append({"log2_messages": lg, "ms": ms, "hashes_per_s": n / (ms * 1e-3),
+                     "roofline_frac_imad": n * w_per_hash(8) / (ms * 1e-3) / peak_w})
+    return {"msg_len": 8, "points": rows}
 
 
 if __name__ == "__main__":

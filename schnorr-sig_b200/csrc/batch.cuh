@@ -58,13 +58,15 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
                                                        const uint8_t* __restrict__ rand32, uint64_t* __restrict__ pts,
                                                        uint32_t* __restrict__ scalars, uint32_t* __restrict__ lin,
                                                        int* __restrict__ bad, const uint32_t* __restrict__ h_in) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t n = in.n;
-    bool live = i < n;
-    uint64_t off = live ? msg_off[i] : 0, len = live ? msg_off[i + 1] - off : 0;
+    bool live = t < n;
+    // threads past the end of the batch redo the block's first item (which always exists) and store nothing: every thread
+    // of the block then reaches the barriers of the permutation
+    size_t i = live ? t : (size_t)blockIdx.x * blockDim.x;
+    uint64_t off = msg_off[i], len = msg_off[i + 1] - off;
     // h_in != nullptr: the challenges were computed by k_batch_challenge_dist (small batches)
-    bool hash_sync = block_uniform_permutations(live && !h_in ? hash_message_permutations(len) : -1);
-    if (!live) return;
+    hash_vote hv = block_hash_vote(!h_in ? hash_message_permutations(len) : -1, off, len);
     uint8_t fl = in.flags[i];
     fp6 sx = load_fp6_planes(in.planes, 0, n, i);
     scalar e = load_scalar_planes(in.planes, 3, n, i);
@@ -77,15 +79,16 @@ __global__ void __launch_bounds__(128, 4) k_batch_prepare(soa_batch in, const ui
     fp6 rx = fp6_zero(), ry = fp6_zero();
     bool r_inf = true;
     if (ok) ok = decompress_point(sx, in.sig_flag[i], rx, ry, r_inf);  // unwrap panic, src/batch.rs:104
-    // every live thread hashes (a malformed item's digest is simply unused): the permutation barriers stay matched,
+    // every thread hashes (a malformed item's digest is simply unused): the permutation barriers stay matched,
     // and the barrier at its start re-aligns the warps after the divergent square-root loops
     scalar h;
     if (h_in) {
 #pragma unroll
         for (int k = 0; k < 8; k++) h.l[k] = h_in[i * 8 + k];
     } else {
-        h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
+        h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hv.sync);
     }
+    if (!live) return;
     if (ok) {
         l = sc_mul(s, e);                     // src/batch.rs:92-97
         s_r = r_inf ? sc_zero() : s;          // identity contributes nothing

@@ -118,7 +118,8 @@ SB_DEV fp_t rescue_inv_sbox(fp_t x) {
 #endif
 // `sync`: block barrier per half-round.  Warps that run the permutation in step share instruction-cache lines (same
 // effect as SB_PHASE_SYNC in the point loops); only legal when EVERY live thread of the block runs the same number of
-// permutations -- the kernels vote on that (block_uniform_permutations) and pass false otherwise.
+// permutations -- the kernels vote on that (block_hash_vote, schnorr_b200.cu) and pass false otherwise; threads without work
+// of their own hash along on a stand-in message so that the whole block reaches every barrier.
 #if defined(__CUDA_ARCH__)
 #define SB_HASH_SYNC(flag) do { if (flag) __syncthreads(); } while (0)
 #else

@@ -122,22 +122,46 @@ __device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
     return v;
 }
 
-// True when every thread of the block that is going to hash (np >= 0) runs the same number of Rescue permutations:
-// the permutation then takes a block barrier per half-round (rescue.cuh), which keeps the warps of the block on the
-// same instruction-cache lines.  Must be called by ALL threads of the block, before any early return.
-__device__ __forceinline__ bool block_uniform_permutations(int np) {
-    __shared__ int s_np_min, s_np_max;
+// Block-wide agreement on the challenge hash.  The permutation takes a block barrier per half-round when every hashing
+// thread of the block runs the same number of Rescue permutations (rescue.cuh: the warps then share instruction-cache
+// lines), and barriers need EVERY thread of the block: threads without work of their own (past the end of the batch,
+// malformed items, identity keys) therefore hash along on the message of the block's first hashing thread and drop the
+// result.  Must be called by all threads of the block.
+//   np         this thread's permutation count, -1 if it has nothing to hash
+//   off / len  in: this thread's message; out: the message to hash (its own, or the first hasher's)
+//   returns    sync  = all hashing threads agree on the count (take the barriers)
+//              any   = at least one thread of the block hashes
+struct hash_vote {
+    bool sync, any;
+};
+__device__ __forceinline__ hash_vote block_hash_vote(int np, uint64_t& off, uint64_t& len) {
+    __shared__ int s_np_min, s_np_max, s_first;
+    __shared__ uint64_t s_off, s_len;
     if (threadIdx.x == 0) {
         s_np_min = 1 << 30;
         s_np_max = -1;
+        s_first = 1 << 30;
     }
     __syncthreads();
     if (np >= 0) {
         atomicMin(&s_np_min, np);
         atomicMax(&s_np_max, np);
+        atomicMin(&s_first, (int)threadIdx.x);
     }
     __syncthreads();
-    return s_np_min >= s_np_max;
+    if ((int)threadIdx.x == s_first) {
+        s_off = off;
+        s_len = len;
+    }
+    __syncthreads();
+    hash_vote v;
+    v.any = s_np_max >= 0;
+    v.sync = v.any && s_np_min >= s_np_max;
+    if (np < 0 && v.any) {
+        off = s_off;
+        len = s_len;
+    }
+    return v;
 }
 
 // AoS -> SoA.  The 81-byte signature records of a block are staged through shared memory with
@@ -259,26 +283,38 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < in.n;
     uint8_t fl = live ? in.flags[i] : FL_MALFORMED;
-    bool hashes = live && !(fl & (FL_MALFORMED | FL_PK_INF));
-    uint64_t off = hashes ? msg_off[i] : 0, len = hashes ? msg_off[i + 1] - off : 0;
-    bool hash_sync = block_uniform_permutations(hashes ? hash_message_permutations(len) : -1);
-    if (!live) return;
-    if (fl & FL_MALFORMED) {
-        verdicts[i] = VERDICT_MALFORMED;
-        return;
+    // `work`: this thread has a verification of its own.  Every other thread of the block (past the end of the batch,
+    // malformed record, identity key) runs the SAME instruction stream on stand-in inputs -- the generator as the key,
+    // zero scalars, the first hashing thread's message -- so that all 128 threads reach every barrier of the hash and of
+    // the point loops; its result is dropped.
+    bool work = live && !(fl & (FL_MALFORMED | FL_PK_INF));
+    uint64_t off = work ? msg_off[i] : 0, len = work ? msg_off[i + 1] - off : 0;
+    hash_vote hv = block_hash_vote(work ? hash_message_permutations(len) : -1, off, len);
+    fp6 sx = fp6_zero(), px, py;
+    scalar e = sc_zero();
+    if (work) {
+        sx = load_fp6_planes(in.planes, 0, in.n, i);
+        e = load_scalar_planes(in.planes, 3, in.n, i);
+        px = load_fp6_planes(in.planes, 5, in.n, i);
+        py = load_fp6_planes(in.planes, 8, in.n, i);
+    } else {  // 1 * G, the first entry of the fixed-base table
+        const uint64_t* g = gtab + (size_t)1 * GTAB_ENTRY_U64;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            px.c[k] = g[k];
+            py.c[k] = g[6 + k];
+        }
     }
-    fp6 sx = load_fp6_planes(in.planes, 0, in.n, i);
-    scalar e = load_scalar_planes(in.planes, 3, in.n, i);
-    fp6 px = load_fp6_planes(in.planes, 5, in.n, i);
-    fp6 py = load_fp6_planes(in.planes, 8, in.n, i);
-    bool pk_inf = fl & FL_PK_INF;
     bool x_ok = !(fl & FL_X_BAD);
     scalar h = sc_zero();
-    if (!pk_inf) {  // an item with a malformed x hashes too (result unused): every hashing thread takes the same barriers
-        h = challenge_scalar(sx, px, py, pk_inf, msgs + off, len, hash_sync);
-        if (!x_ok) h = sc_zero();
+    if (hv.any) {  // block-uniform.  An item with a malformed x hashes too (result unused)
+        h = challenge_scalar(sx, px, py, false, msgs + off, len, hv.sync);
+        if (!x_ok || !work) h = sc_zero();
     }
-    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf, h, gtab, &s_d[threadIdx.x].p);
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, false, h, gtab, &s_d[threadIdx.x].p);
+    if (!live) return;
+    if (fl & FL_MALFORMED) v = VERDICT_MALFORMED;
+    else if (fl & FL_PK_INF) v = VERDICT_NEEDS_EXACT;   // the identity key is the exact kernel's business
     verdicts[i] = v;
     if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
 }
@@ -348,10 +384,11 @@ __global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;
     uint64_t off = live ? msg_off[i] : 0, len = live ? msg_off[i + 1] - off : 0;
-    bool hash_sync = block_uniform_permutations(live ? hash_message_permutations(len) : -1);
-    if (!live) return;
-    const uint64_t* r = reinterpret_cast<const uint64_t*>(rx48 + i * 48);
-    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + i * 96);
+    // threads past the end of the batch hash the first live thread's message along (every thread reaches the barriers)
+    hash_vote hv = block_hash_vote(live ? hash_message_permutations(len) : -1, off, len);
+    size_t src = live ? i : (size_t)blockIdx.x * blockDim.x;   // the block's first item always exists
+    const uint64_t* r = reinterpret_cast<const uint64_t*>(rx48 + src * 48);
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(pk96 + src * 96);
     fp6 rx, px;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -360,7 +397,8 @@ __global__ void __launch_bounds__(HASH_THREADS) k_hash(size_t n, const uint8_t* 
     }
     fp_t py0 = p[6];
     fp_t d[4];
-    hash_message(rx, px, py0, msgs + off, len, d, hash_sync);
+    hash_message(rx, px, py0, msgs + off, len, d, hv.sync);
+    if (!live) return;
     ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + i * 32);
     o[0] = make_ulonglong2(d[0], d[1]);
     o[1] = make_ulonglong2(d[2], d[3]);
