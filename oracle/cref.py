@@ -29,6 +29,33 @@ def build(force: bool = False) -> str:
     return so
 
 
+_FAST = None
+
+
+def fast_lib():
+    """oracle/libcfast.so: the OPTIMISED CPU port (oracle/cfast.c) -- bench baseline, cross-checked against cref.c."""
+    global _FAST
+    if _FAST is None:
+        so = os.path.join(_HERE, "libcfast.so")
+        src = os.path.join(_HERE, "cfast.c")
+        hdr = os.path.join(_HERE, "..", "include", "cheetah_params.h")
+        if (not os.path.exists(so)) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr)):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libcfast.so"], stdout=subprocess.DEVNULL)
+        _FAST = C.CDLL(so)
+    return _FAST
+
+
+def verify_many_fast(sigs, pks, pk_inf, msgs, off, nthreads=1):
+    """Signature::verify for n items through the optimised port; same verdict codes as verify_many."""
+    sigs, pks, msgs = _u8(sigs), _u8(pks), _u8(msgs)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = sigs.shape[0]
+    inf = None if pk_inf is None else _u8(pk_inf)
+    out = np.zeros(n, dtype=np.uint8)
+    fast_lib().cfast_verify_many(C.c_uint64(n), _p(sigs), _p(pks), _p(inf), _p(msgs), _p(off), _p(out), C.c_int(nthreads))
+    return out
+
+
 def lib():
     global _LIB
     if _LIB is None:

@@ -224,3 +224,32 @@ def test_upstream_dump_known_answers_when_present():
         assert pk == (o._limbs_from_hex(s_["public_key"]["x"]), o._limbs_from_hex(s_["public_key"]["y"]))
         sig = bytes.fromhex(s_["signature"])
         assert o.verify(sig[:49], int.from_bytes(sig[49:], "little"), bytes.fromhex(s_["msg"]), pk) == 0
+
+
+def test_optimised_cpu_port_agrees_with_the_textbook_oracle():
+    """oracle/cfast.c (windowed NAFs, Straus-Shamir with a base-point table, lazy reduction: the CPU arm of bench.py)
+    returns the verdicts of oracle/cref.c on valid, faulty, malformed and adversarial inputs."""
+    import cref
+    from util import KAT96, make_workload, pt_to96
+    n = 260
+    w = make_workload(303, n, lens=[int(x) for x in np.random.default_rng(303).integers(0, 170, n)])
+    sigs, pk, inf = w["sigs"].copy(), w["pk"].copy(), w["inf"].copy()
+    order = o.COFACTOR * o.Q
+    kat = (o.KAT_X, o.KAT_Y)
+    sigs[5, 49] ^= 1                                   # wrong e
+    pk[9] = KAT96                                      # off-subgroup key
+    sigs[11, :48] = 0; sigs[11, 48] = 0x80             # x := identity encoding
+    sigs[13, 8:16] = 0xFF                              # non-canonical limb
+    sigs[17, 49 + 31] = 0xFF                           # e >= q
+    inf[19] = 1                                        # identity key
+    sigs[23, 49:] = 0                                  # e := 0
+    pk[29] = pt_to96(o.pt_mul(kat, order // 2))        # order 2
+    pk[31] = pt_to96(o.pt_mul(kat, order // 29))       # order 29
+    pk[37] = pt_to96(o.pt_add(o.generator(), o.pt_mul(kat, order // 2)))   # order 2q
+    pk[41, 8:16] = 0xFF                                # non-canonical key limb
+    pk[43], pk[44] = w["pk"][44].copy(), w["pk"][43].copy()
+    nt = cref.default_threads()
+    a = cref.verify_many(sigs, pk, inf, w["blob"], w["off"], nt)
+    b = cref.verify_many_fast(sigs, pk, inf, w["blob"], w["off"], nt)
+    assert np.array_equal(a, b)
+    assert {0, 1, 2, 3} == set(int(v) for v in a)
