@@ -333,8 +333,7 @@ enum fast_result : int {
 SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const scalar& e,
                             const uint64_t* __restrict__ gtab, jf_pt* R, jf_pt* Dp) {
     jf_pt Bq[8], Bh[8];
-    int8_t hd[64];
-    recode_signed_w4(h, hd);
+    int h_carry = 0;  // signed 4-bit digits of h are recoded on the fly (recode_signed_w4), least significant first
     uint32_t q_seen = 0, h_seen = 0;
     bool exc = false;
 #pragma unroll 1
@@ -360,7 +359,9 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             }
         }
         if ((j & 3) == 0) {
-            int dh = hd[j >> 2];
+            int raw = (int)((h.l[j >> 5] >> (j & 31)) & 15) + h_carry;   // j = 4 i: nibble i of h
+            h_carry = raw > 8;
+            int dh = h_carry ? raw - 16 : raw;
             int mag = dh < 0 ? -dh : dh;
             int idx = mag ? mag - 1 : 0;
             exc |= jf_add<true>(&Bh[idx], Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
@@ -370,7 +371,13 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     }
     // Bucket aggregation (R_k = sum_{m>=k} B_m, O_k = sum_{m>=k} R_m):
     //   q (odd digits 2k+1):  [q]P = 2 O_1 + R_0        h (digits m = k+1):  h*P = O_0
-    jf_pt Rq = Bq[7], Oq = Bq[7], Rh = Bh[7], Oh = Bh[7];
+    // The running sums R live IN PLACE in the top buckets and O_h in the caller's result slot: no extra copies in
+    // thread-local memory (the buckets are not needed any more once they have been folded in).
+    jf_pt* Rq = &Bq[7];
+    jf_pt* Rh = &Bh[7];
+    jf_pt* Oh = R;
+    jf_pt Oq = Bq[7];
+    *Oh = Bh[7];
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
     // `same_h`: O_h and R_h are the same (finite) point.  It happens whenever the buckets below the highest used
     // digit magnitude are empty (~2e-4 of random challenges): O += R is then a doubling, taken on a divergent
@@ -380,21 +387,21 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     for (int b = 6; b >= 0; b--) {
         SB_PHASE_SYNC(1);
         bool eb = !((q_seen >> b) & 1);
-        exc |= jf_add<true>(&Rq, &Bq[b], jf_add_mode(eRq, eb, false));
+        exc |= jf_add<true>(Rq, &Bq[b], jf_add_mode(eRq, eb, false));
         eRq = eRq && eb;
         if (b >= 1) {
-            exc |= jf_add<true>(&Oq, &Rq, jf_add_mode(eOq, eRq, false));
+            exc |= jf_add<true>(&Oq, Rq, jf_add_mode(eOq, eRq, false));
             eOq = eOq && eRq;
         }
         eb = !((h_seen >> b) & 1);
-        exc |= jf_add<true>(&Rh, &Bh[b], jf_add_mode(eRh, eb, false));
+        exc |= jf_add<true>(Rh, &Bh[b], jf_add_mode(eRh, eb, false));
         if (!eb && !eRh) same_h = false;  // a real addition changed R
         eRh = eRh && eb;
         if (__builtin_expect(same_h && !eOh, 0)) {
-            exc |= jf_dbl<true>(&Oh);           // O == R: O + R = 2 O
+            exc |= jf_dbl<true>(Oh);           // O == R: O + R = 2 O
             same_h = false;
         } else {
-            exc |= jf_add<true>(&Oh, &Rh, jf_add_mode(eOh, eRh, false));
+            exc |= jf_add<true>(Oh, Rh, jf_add_mode(eOh, eRh, false));
             same_h = eOh && !eRh;         // O was empty and has just been set to R
         }
         eOh = eOh && eRh;
@@ -403,12 +410,11 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     else exc |= jf_dbl<true>(&Oq);
     // [q]P = 2 O_1 + R_0 is the identity  <=>  2 O_1 == -R_0
     bool x_eq;
-    bool torsion_free = jf_eq_neg(Oq, Rq, x_eq);
+    bool torsion_free = jf_eq_neg(Oq, *Rq, x_eq);
     if (x_eq && !torsion_free) exc = true;  // 2 O_1 == R_0: a doubling the fast path does not evaluate
 
-    // + e*G: 20 table points (affine, w = 1) added to h*P
+    // + e*G: 20 table points (affine, w = 1) added to h*P (which already sits in *R)
     bool e_acc = eOh;
-    *R = Oh;
     {
         int carry = 0;
         jf_pt T;

@@ -104,15 +104,20 @@ struct soa_batch {
     size_t n;
 };
 
+// The planes are read exactly once per launch: streaming loads (evict-first) keep them from displacing the thread-local
+// bucket lines that the L2 is really caching in these kernels.
+__device__ __forceinline__ ulonglong2 load_plane(const ulonglong2* p) {
+    return __ldcs(p);
+}
 __device__ __forceinline__ fp6 load_fp6_planes(const ulonglong2* planes, int first_plane, size_t n, size_t i) {
-    ulonglong2 a = planes[(size_t)(first_plane + 0) * n + i];
-    ulonglong2 b = planes[(size_t)(first_plane + 1) * n + i];
-    ulonglong2 c = planes[(size_t)(first_plane + 2) * n + i];
+    ulonglong2 a = load_plane(&planes[(size_t)(first_plane + 0) * n + i]);
+    ulonglong2 b = load_plane(&planes[(size_t)(first_plane + 1) * n + i]);
+    ulonglong2 c = load_plane(&planes[(size_t)(first_plane + 2) * n + i]);
     return fp6{{a.x, a.y, b.x, b.y, c.x, c.y}};
 }
 __device__ __forceinline__ scalar load_scalar_planes(const ulonglong2* planes, int first_plane, size_t n, size_t i) {
-    ulonglong2 a = planes[(size_t)(first_plane + 0) * n + i];
-    ulonglong2 b = planes[(size_t)(first_plane + 1) * n + i];
+    ulonglong2 a = load_plane(&planes[(size_t)(first_plane + 0) * n + i]);
+    ulonglong2 b = load_plane(&planes[(size_t)(first_plane + 1) * n + i]);
     return sc_from_u64x4(a.x, a.y, b.x, b.y);
 }
 __device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
