@@ -280,11 +280,50 @@ SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
     return wanted && n == 0;
 }
 
+// acc <- acc (+|-) (x2, y2) for an AFFINE addend (denominator 1): the mixed form of jf_add<true> -- no powers of w2,
+// U1 = X1 and S1 = Y1 need no scaling (14 base-field products less), the same lazily accumulated X3 / Y3.
+// `acc` must be finite.  Returns true (acc untouched) when x(acc) == x2.
+SB_DEV_NOINLINE bool jf_madd(jf_pt* acc, const jf_pt* t, bool neg) {
+    fp6 X1 = acc->X, Y1 = acc->Y, X2 = t->X, Y2 = t->Y;
+    fp_t w1 = acc->w;
+    fp_t w1s = fp_sqr_nc(w1), w1c = fp_mul_nc(w1s, w1);
+    fp6 d, num;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        wide_acc w;
+        wide_set64(w, X1.c[i]);                       // U1 - U2 = X1 - x2 w1^2
+        wide_mac(w, FP_P - X2.c[i], w1s);
+        d.c[i] = wide_reduce(w);
+        wide_set64(w, Y1.c[i]);                       // S1 - (+|-) S2 = Y1 -+ y2 w1^3
+        wide_mac(w, neg ? Y2.c[i] : FP_P - Y2.c[i], w1c);
+        num.c[i] = wide_reduce_nc(w);
+    }
+    fp6 c;
+    fp_t n;
+    fp6_cofactor_norm(&d, &c, &n);
+    fp6 L = fp6_mul_nc(num, c);                       // slope = L / (n w1)
+    fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
+    fp6 A = fp6_scale(X1, n2);                        // x1 w3^2
+    fp6 X3 = fp6_sqr_sub_scaled(L, A, X2, fp_mul_nc(n2, w1s));
+    fp6 Y3 = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y1, n3);
+    if (n == 0) return true;
+    acc->X = X3;
+    acc->Y = Y3;
+    acc->w = fp_mul(n, w1);
+    return false;
+}
+
 // Exact accumulation for the Pippenger buckets (batch.cuh): acc += (+|-) t with t affine (t->w == 1).
 // The identity is w == 0; P + P and P - P (repeated signers put equal points into one bucket,
 // src/batch.rs:167-169) are resolved on a rarely taken branch.
 SB_DEV void jf_madd_exact(jf_pt* acc, const jf_pt* t, bool neg) {
-    bool exc = jf_add(acc, t, jf_add_mode(acc->w == 0, false, neg));
+    if (acc->w == 0) {  // first point of the bucket
+        acc->X = t->X;
+        acc->Y = neg ? fp6_neg(t->Y) : t->Y;
+        acc->w = 1;
+        return;
+    }
+    bool exc = jf_madd(acc, t, neg);
     if (__builtin_expect(exc, 0)) {
         fp_t w = acc->w;
         fp6 ty = fp6_scale(neg ? fp6_neg(t->Y) : t->Y, fp_mul_nc(fp_sqr_nc(w), w));

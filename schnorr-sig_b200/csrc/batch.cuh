@@ -876,7 +876,10 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
     cudaEventRecord(ctx->ev_k1, st);
     k_msm_segment_fixup<<<grid_for(nslots, 128), 128, 0, st>>>(pl, (uint32_t)nslots, T, offsets, counts,
                                                                (seg_partial*)d_parts, buckets, long_list, long_count);
-    k_msm_fixup_long<<<(unsigned)(max_long < 1024 ? max_long : 1024), FIXUP_LONG_THREADS, 0, st>>>(
+    // long buckets are rare (sparse top window, repeated randomisers): a grid of two blocks per SM strides over the list;
+    // a larger grid only adds block-launch latency to the common case of an empty list (65 us at 1024 blocks)
+    size_t long_grid = (size_t)2 * ctx->sm_count;
+    k_msm_fixup_long<<<(unsigned)(max_long < long_grid ? max_long : long_grid), FIXUP_LONG_THREADS, 0, st>>>(
         pl, T, offsets, counts, (seg_partial*)d_parts, buckets, long_list, long_count);
     k_msm_window_sum<<<grid_for((size_t)pl.K * pl.chunks, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(pl, buckets, chunk_out);
     k_msm_window_fold<<<pl.K, FOLD_THREADS, 0, st>>>(pl, chunk_out, windows);
