@@ -63,11 +63,11 @@ static int multi_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
                              const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
     CHECK_MSG_OFF(ctx, n, msg_off);
     auto sl = multi_slices(ctx, n);
+    // the hot entry point: every shard gets its slice of the caller's offset table as it is (validated once, above; no
+    // per-shard rebasing pass over the offsets)
     return multi_run(ctx, sl, [&](int k, shard_slice s) {
-        auto off = rebase_offsets(msg_off, s.lo, s.hi);
-        return schnorr_b200_verify_many(ctx->shards[k], s.hi - s.lo, sigs81 + 81 * s.lo, pk96 + 96 * s.lo,
-                                        pk_inf ? pk_inf + s.lo : nullptr, msgs ? msgs + msg_off[s.lo] : nullptr, off.data(),
-                                        verdicts + s.lo);
+        return verify_many_host(ctx->shards[k], s.hi - s.lo, sigs81 + 81 * s.lo, pk96 + 96 * s.lo,
+                                pk_inf ? pk_inf + s.lo : nullptr, msgs, msg_off + s.lo, verdicts + s.lo);
     });
 }
 static int multi_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,

@@ -772,6 +772,8 @@ static int stage_in(schnorr_b200_ctx* ctx, int slot, const void* host, size_t by
         }                                                                                                          \
     } while (0)
 
+static int verify_many_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96, const uint8_t* pk_inf,
+                            const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts);
 #include "batch.cuh"
 #include "multi.cuh"
 
@@ -1086,9 +1088,18 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
     MULTI_DISPATCH(ctx, multi_verify_many(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, verdicts));
     if (!ctx || (n && (!sigs81 || !pk96 || !msg_off || !verdicts))) return SCHNORR_B200_EARG;
     if (n == 0) return SCHNORR_B200_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CHECK_MSG_OFF(ctx, n, msg_off);
-    size_t mb = msg_off[n];
+    return verify_many_host(ctx, n, sigs81, pk96, pk_inf, msgs, msg_off, verdicts);
+}
+} // extern "C" (the internal host pipeline below has C++ linkage; it is declared before multi.cuh)
+
+// The pipelined host path on ONE device.  `msg_off` is a VALIDATED, non-decreasing table of n + 1 offsets into `msgs`
+// whose first entry may be non-zero: the multi-device layer hands every shard its slice of the caller's table as it is.
+static int verify_many_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96,
+                            const uint8_t* pk_inf, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t base = msg_off[0];
+    size_t mb = msg_off[n] - base;
     if (mb && !msgs) return SCHNORR_B200_EARG;
     void *d_sig, *d_pk, *d_inf = nullptr, *d_m, *d_off, *d_out;
     if (int rc = ensure_scratch(ctx, SL_D, n * 81, &d_sig)) return rc;
@@ -1129,7 +1140,7 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_pk + 96 * lo, pk96 + 96 * lo, cn * 96, cudaMemcpyHostToDevice, cs));
         if (pk_inf) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_inf + lo, pk_inf + lo, cn, cudaMemcpyHostToDevice, cs));
         size_t b0 = msg_off[lo], b1 = msg_off[hi];
-        if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_m + b0, msgs + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+        if (b1 > b0) CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)d_m + (b0 - base), msgs + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[c], cs));
         // consecutive chunks run on alternating compute streams: the blocks of chunk c + 1 start on the SMs that chunk c
         // is draining instead of waiting for its last block (chunks touch disjoint regions of every buffer)
@@ -1143,7 +1154,8 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
         k_ingest<<<grid_for(cn, INGEST_THREADS), INGEST_THREADS, 0, st>>>(cn, (uint8_t*)d_sig + 81 * lo, (uint8_t*)d_pk + 96 * lo,
                                                                          pk_inf ? (uint8_t*)d_inf + lo : nullptr, sc);
         if (st == ks) cudaEventRecord(ctx->ev_k0, ks);
-        if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, st)) return rc;
+        // the kernels index the message blob with the caller's absolute offsets: shift the device base accordingly
+        if (int rc = launch_verify(ctx, sc, (uint8_t*)d_m - base, (uint64_t*)d_off + lo, (uint8_t*)d_out + lo, lo, c, n, st)) return rc;
         if (st == ks) cudaEventRecord(ctx->ev_k1, ks);
         ctx->launches += 1;
     }
@@ -1159,6 +1171,7 @@ int schnorr_b200_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sig
     CUDA_TRY(ctx, cudaStreamSynchronize(ks));
     return SCHNORR_B200_OK;
 }
+extern "C" {
 
 // ---- KeyedSignature::verify over wire records -------------------------------------------------
 int schnorr_b200_verify_keyed_many_dev(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,
