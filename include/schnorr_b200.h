@@ -90,6 +90,9 @@ int schnorr_b200_last_exact_count(schnorr_b200_ctx *ctx, uint64_t *count);
  * six lanes: ~4x lower latency, 6x more parallelism per signature, ~1.5x the work); larger calls the one-signature-per-
  * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 10240 (measured crossover ~12 k). */
 int schnorr_b200_set_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
+/* Batches of at most `max_signatures` compute their challenges with one signature per six lanes ahead of the (then
+ * hash-free) prepare kernel; larger ones hash one signature per thread.  Default 2^18 (measured crossover). */
+int schnorr_b200_set_batch_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
 /* Test hook: force the Pippenger window width (4..16, 0 = planner's choice) and the segment length of the bucket
  * accumulation (>= 8, 0 = automatic) of the batch path, to exercise the skewed-bucket code paths. */
 int schnorr_b200_set_msm_geometry(schnorr_b200_ctx *ctx, int window_bits, unsigned segment_len);

@@ -53,6 +53,7 @@ struct schnorr_b200_ctx {
     int last_msm_c = 0, last_msm_K = 0;             // Pippenger geometry of the last batch call (schnorr_b200_last_batch_plan)
     uint32_t last_msm_T = 0;
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
+    size_t batch_dist_max = (size_t)1 << 18;        // batches up to this size hash their challenges on six lanes per signature
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
@@ -979,6 +980,12 @@ int schnorr_b200_set_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures
     if (!ctx) return SCHNORR_B200_EARG;
     for (schnorr_b200_ctx* sh : ctx->shards) sh->dist_max = max_signatures;
     ctx->dist_max = max_signatures;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_set_batch_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    ctx->batch_dist_max = max_signatures;
+    for (schnorr_b200_ctx* sh : ctx->shards) sh->batch_dist_max = max_signatures;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_set_msm_geometry(schnorr_b200_ctx* ctx, int window_bits, unsigned segment_len) {
