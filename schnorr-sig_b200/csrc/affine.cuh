@@ -367,18 +367,27 @@ enum fast_result : int {
 };
 
 // [q]P == O ?  and  R = h*P + e*G, sharing the doubling chain D_j = 2^j P as torsion_check_and_mul does, in the
-// (X, Y, w) coordinates above.  `Dp` is caller-provided storage for D_j (shared memory in the kernels).
+// (X, Y, w) coordinates above.  Caller-provided storage (shared memory in the kernels): `Dp` for D_j, and `Bh` for the
+// buckets of the challenge digits of magnitude 1..FAST_BH_SHARED -- bucket b of this thread at Bh[b * bh_stride].  Those
+// buckets are indexed by a PER-THREAD digit: in thread-local memory a warp's 32 accesses scatter over 32 different
+// lines (ncu: 13 of 32 bytes per sector used, 7 GB of DRAM write-backs per 2^20 signatures, 5 % of the kernel time),
+// in shared memory the 104-byte slots are conflict-free for 64-bit accesses whatever the bucket index is
+// (bank = 26 tid + 2 k mod 32: sixteen distinct even banks per half-warp).  The buckets of the subgroup check are
+// indexed by the constant digits of q -- warp-uniform, hence coalesced -- and stay in thread-local memory, as does the
+// bucket of magnitude 8 (one digit in sixteen; two blocks of 128 threads x 8 slots fill the SM's shared memory).
 // On FAST_TORSION_FREE / FAST_NOT_TORSION_FREE, *R is the result (never the identity: that is reported as exceptional).
+static constexpr int FAST_BH_SHARED = 7;
 SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const scalar& e,
-                            const uint64_t* __restrict__ gtab, jf_pt* R, jf_pt* Dp) {
-    jf_pt Bq[8], Bh[8];
+                            const uint64_t* __restrict__ gtab, jf_pt* R, jf_pt* Dp, jf_pt* Bh, int bh_stride) {
+    jf_pt Bq[8], Bh8;
+#define SB_BH(b) ((b) < FAST_BH_SHARED ? Bh + (size_t)(b) * bh_stride : &Bh8)
     int h_carry = 0;  // signed 4-bit digits of h are recoded on the fly (recode_signed_w4), least significant first
     uint32_t q_seen = 0, h_seen = 0;
     bool exc = false;
 #pragma unroll 1
     for (int b = 0; b < 8; b++) {  // dummy (masked) operations read empty buckets: give them defined contents
         Bq[b] = jf_pt{fp6_zero(), fp6_zero(), 1};
-        Bh[b] = Bq[b];
+        *SB_BH(b) = Bq[b];
     }
     Dp->X = px;
     Dp->Y = py;
@@ -403,7 +412,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             int dh = h_carry ? raw - 16 : raw;
             int mag = dh < 0 ? -dh : dh;
             int idx = mag ? mag - 1 : 0;
-            exc |= jf_add<true>(&Bh[idx], Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
+            exc |= jf_add<true>(SB_BH(idx), Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
             if (mag) h_seen |= 1u << idx;
         }
         if (j < 255) exc |= jf_dbl<true>(Dp);
@@ -413,10 +422,10 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     // The running sums R live IN PLACE in the top buckets and O_h in the caller's result slot: no extra copies in
     // thread-local memory (the buckets are not needed any more once they have been folded in).
     jf_pt* Rq = &Bq[7];
-    jf_pt* Rh = &Bh[7];
+    jf_pt* Rh = &Bh8;
     jf_pt* Oh = R;
     jf_pt Oq = Bq[7];
-    *Oh = Bh[7];
+    *Oh = Bh8;
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
     // `same_h`: O_h and R_h are the same (finite) point.  It happens whenever the buckets below the highest used
     // digit magnitude are empty (~2e-4 of random challenges): O += R is then a doubling, taken on a divergent
@@ -433,7 +442,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             eOq = eOq && eRq;
         }
         eb = !((h_seen >> b) & 1);
-        exc |= jf_add<true>(Rh, &Bh[b], jf_add_mode(eRh, eb, false));
+        exc |= jf_add<true>(Rh, SB_BH(b), jf_add_mode(eRh, eb, false));
         if (!eb && !eRh) same_h = false;  // a real addition changed R
         eRh = eRh && eb;
         if (__builtin_expect(same_h && !eOh, 0)) {
@@ -482,6 +491,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
         }
     }
     if (e_acc) exc = true;  // the result is the identity: exact routine
+#undef SB_BH
     if (exc) return FAST_EXCEPTIONAL;
     return torsion_free ? FAST_TORSION_FREE : FAST_NOT_TORSION_FREE;
 }

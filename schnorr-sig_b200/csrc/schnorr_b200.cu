@@ -276,16 +276,19 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
 #ifndef VERIFY_FAST_MIN_BLOCKS
 #define VERIFY_FAST_MIN_BLOCKS 2
 #endif
+static constexpr size_t VERIFY_FAST_SMEM = (size_t)(1 + FAST_BH_SHARED) * VERIFY_THREADS * sizeof(jf_pt);  // 106 496 B: two blocks per SM
 __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_verify_fast(soa_batch in, const uint8_t* __restrict__ msgs,
                                                            const uint64_t* __restrict__ msg_off,
                                                            const uint64_t* __restrict__ gtab,
                                                            uint8_t* __restrict__ verdicts,
                                                            uint32_t* __restrict__ work_list,
                                                            uint32_t* __restrict__ work_count) {
-    struct d_slot {
-        jf_pt p;  // 104 B per thread: 2-way bank conflicts at most
-    };
-    __shared__ d_slot s_d[VERIFY_THREADS];
+    // dynamic shared memory (VERIFY_FAST_SMEM bytes): the running point D_j of every thread, then FAST_BH_SHARED
+    // challenge buckets per thread, bucket-major.  A slot is 104 bytes: 64-bit accesses of a half-warp fall into sixteen
+    // distinct even banks whatever bucket each thread addresses.
+    extern __shared__ __align__(16) unsigned char s_fast[];
+    jf_pt* s_d = reinterpret_cast<jf_pt*>(s_fast);
+    jf_pt* s_bh = s_d + VERIFY_THREADS;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < in.n;
     uint8_t fl = live ? in.flags[i] : FL_MALFORMED;
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
         h = challenge_scalar(sx, px, py, false, msgs + off, len, hv.sync);
         if (!x_ok || !work) h = sc_zero();
     }
-    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, false, h, gtab, &s_d[threadIdx.x].p);
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, false, h, gtab, s_d + threadIdx.x, s_bh + threadIdx.x, VERIFY_THREADS);
     if (!live) return;
     if (fl & FL_MALFORMED) v = VERDICT_MALFORMED;
     else if (fl & FL_PK_INF) v = VERDICT_NEEDS_EXACT;   // the identity key is the exact kernel's business
@@ -801,7 +804,7 @@ static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint
         k_verify_dist<<<grid_for(soa.n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list,
                                                                                    counters + counter);
     else
-        k_verify_fast<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+        k_verify_fast<<<grid, VERIFY_THREADS, VERIFY_FAST_SMEM, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
     // the exact kernel sizes itself from the device-side counter: blocks beyond it exit at once
     k_verify<<<grid, VERIFY_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
     ctx->launches += 2;
@@ -856,7 +859,9 @@ int schnorr_b200_create(int device, schnorr_b200_ctx** out) {
     ctx->stream = ctx->own_stream;
     {
         int per_sm = 0;
-        CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verify_fast, VERIFY_THREADS, 0));
+        CREATE_TRY(cudaFuncSetAttribute(k_verify_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VERIFY_FAST_SMEM));
+        CREATE_TRY(cudaFuncSetAttribute(k_verify_fast, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_verify_fast, VERIFY_THREADS, VERIFY_FAST_SMEM));
         if (per_sm < 1) per_sm = 1;
         ctx->verify_wave = (size_t)ctx->sm_count * per_sm * VERIFY_THREADS;
     }

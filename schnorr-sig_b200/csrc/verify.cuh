@@ -33,12 +33,14 @@ SB_DEV uint8_t verify_points(const fp6& sig_x, bool x_ok, const scalar& e, const
 }
 
 // Same verdicts through the fast path in (X, Y, w) coordinates (affine.cuh).  VERDICT_NEEDS_EXACT asks the caller to run
-// verify_points on this item: identity key, or an exceptional case of the chord-and-tangent formulas.
+// verify_points on this item: identity key, or an exceptional case of the chord-and-tangent formulas.  `d_storage` /
+// `bh_storage`: the caller's slots for the running point and the challenge buckets (affine.cuh: verify_core_fast).
 SB_DEV uint8_t verify_points_fast(const fp6& sig_x, bool x_ok, const scalar& e, const fp6& pk_x, const fp6& pk_y, bool pk_inf,
-                                  const scalar& h, const uint64_t* __restrict__ gtab, jf_pt* d_storage) {
+                                  const scalar& h, const uint64_t* __restrict__ gtab, jf_pt* d_storage, jf_pt* bh_storage,
+                                  int bh_stride) {
     if (pk_inf) return VERDICT_NEEDS_EXACT;
     jf_pt r;
-    int fr = verify_core_fast(pk_x, pk_y, h, e, gtab, &r, d_storage);
+    int fr = verify_core_fast(pk_x, pk_y, h, e, gtab, &r, d_storage, bh_storage, bh_stride);
     if (fr == FAST_EXCEPTIONAL) return VERDICT_NEEDS_EXACT;
     if (fr == FAST_NOT_TORSION_FREE) return VERDICT_INVALID_PUBLIC_KEY;
     if (!x_ok) return VERDICT_MALFORMED;

@@ -180,10 +180,10 @@ API int hs_verify_core_fast(const uint8_t* p96, const uint8_t* h32, const uint8_
     fp6 x, y;
     memcpy(x.c, p96, 48);
     memcpy(y.c, p96 + 48, 48);
-    jf_pt r, d;
+    jf_pt r, d, bh[FAST_BH_SHARED];
     memset(&r, 0, sizeof r);
     r.w = 1;
-    int fr = verify_core_fast(x, y, ldsc(h32), ldsc(e32), g_gtab.data(), &r, &d);
+    int fr = verify_core_fast(x, y, ldsc(h32), ldsc(e32), g_gtab.data(), &r, &d, bh, 1);
     // normalise (X, Y, w) for the comparison with the oracle
     fp_t wi = fp_inv(fp_canon(r.w)), wi2 = fp_sqr(wi);
     fp6 ax = fp6_scale(r.X, wi2), ay = fp6_scale(r.Y, fp_mul(wi2, wi));
@@ -206,8 +206,8 @@ API int hs_verify_one_fast(const uint8_t* sig81, const uint8_t* pk96, int pk_inf
     if ((!pk_ok && !pk_inf) || sc_geq_q(e)) return VERDICT_MALFORMED;
     scalar h = sc_zero();
     if (x_ok) h = challenge_scalar(sx, px, py, pk_inf != 0, msg, len);
-    jf_pt da;
-    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &da);
+    jf_pt da, bh[FAST_BH_SHARED];
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, pk_inf != 0, h, g_gtab.data(), &da, bh, 1);
     if (v != VERDICT_NEEDS_EXACT) return v;
     *used_exact = 1;
     jac_pt d;
