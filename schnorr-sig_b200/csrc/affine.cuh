@@ -92,9 +92,18 @@ SB_DEV fp3 fp3_mul_pre(const fp3& a, const fp3& b, fp_t b7_1, fp_t b7_2) {
 //   reductions, no subtraction: the y terms enter through p - y_i):
 //     N0 = x0^2 + 2 x1 7x2 - 2 y0 7y2 - y1 7y1      N1 = 2 x0 x1 + x2 7x2 - y0^2 - 2 y1 7y2
 //     N2 = 2 x0 x2 + x1^2 - 2 y0 y1 - y2 7y2
-SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
+// Operand and results travel in registers (a by-value struct): the pointer form cost a 13-word round trip through
+// thread-local memory per call (403 calls per verification; ncu: 0.7 % of the kernel in load stalls behind them).
+struct fp6_cof {
+    fp6 c;
+    fp_t n;
+};
+SB_DEV_NOINLINE fp6_cof fp6_cofactor_norm_v(fp6 d) {
+    fp6_cof out;
+    fp6* c = &out.c;
+    fp_t* n = &out.n;
     fp3 x, y, adj;
-    fp6_split(*d, x, y);
+    fp6_split(d, x, y);
     fp3 ny = fp3{{FP_P - y.c[0], FP_P - y.c[1], FP_P - y.c[2]}};
     fp_t x2_7 = fp_mul7_nc(x.c[2]), y1_7 = fp_mul7_nc(y.c[1]), y2_7 = fp_mul7_nc(y.c[2]);
     fp3 nn;
@@ -123,6 +132,12 @@ SB_DEV_NOINLINE void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
     fp3_adj_norm_lazy(nn, adj, *n);  // 1/N = adj / n
     fp_t adj7_1 = fp_mul7_nc(adj.c[1]), adj7_2 = fp_mul7_nc(adj.c[2]);
     *c = fp6_join(fp3_mul_pre(x, adj, adj7_1, adj7_2), fp3_mul_pre(ny, adj, adj7_1, adj7_2));
+    return out;
+}
+SB_DEV void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
+    fp6_cof r = fp6_cofactor_norm_v(*d);
+    *c = r.c;
+    *n = r.n;
 }
 
 // a * s for s in Fp (any 64-bit representative)
@@ -376,12 +391,16 @@ enum fast_result : int {
 // indexed by the constant digits of q -- warp-uniform, hence coalesced -- and stay in thread-local memory, as does the
 // bucket of magnitude 8 (one digit in sixteen; two blocks of 128 threads x 8 slots fill the SM's shared memory).
 // On FAST_TORSION_FREE / FAST_NOT_TORSION_FREE, *R is the result (never the identity: that is reported as exceptional).
-static constexpr int FAST_BH_SHARED = 7;
+#ifndef SB_FAST_BH_SHARED
+#define SB_FAST_BH_SHARED 7
+#endif
+static constexpr int FAST_BH_SHARED = SB_FAST_BH_SHARED;
 SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const scalar& e,
                             const uint64_t* __restrict__ gtab, jf_pt* R, jf_pt* Dp, jf_pt* Bh, int bh_stride) {
-    jf_pt Bq[8], Bh8;
-#define SB_BH(b) ((b) < FAST_BH_SHARED ? Bh + (size_t)(b) * bh_stride : &Bh8)
+    jf_pt Bq[8], Bhl[FAST_BH_SHARED < 8 ? 8 - FAST_BH_SHARED : 1];
+#define SB_BH(b) ((b) < FAST_BH_SHARED ? Bh + (size_t)(b) * bh_stride : &Bhl[(b) - (FAST_BH_SHARED < 8 ? FAST_BH_SHARED : 7)])
     int h_carry = 0;  // signed 4-bit digits of h are recoded on the fly (recode_signed_w4), least significant first
+    scalar hs = h;    // shifted right by one nibble per window: a dynamically indexed h.l[j >> 5] would live in local memory
     uint32_t q_seen = 0, h_seen = 0;
     bool exc = false;
 #pragma unroll 1
@@ -407,7 +426,10 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             }
         }
         if ((j & 3) == 0) {
-            int raw = (int)((h.l[j >> 5] >> (j & 31)) & 15) + h_carry;   // j = 4 i: nibble i of h
+            int raw = (int)(hs.l[0] & 15) + h_carry;   // j = 4 i: nibble i of h
+#pragma unroll
+            for (int k = 0; k < 7; k++) hs.l[k] = (hs.l[k] >> 4) | (hs.l[k + 1] << 28);
+            hs.l[7] >>= 4;
             h_carry = raw > 8;
             int dh = h_carry ? raw - 16 : raw;
             int mag = dh < 0 ? -dh : dh;
@@ -422,10 +444,10 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     // The running sums R live IN PLACE in the top buckets and O_h in the caller's result slot: no extra copies in
     // thread-local memory (the buckets are not needed any more once they have been folded in).
     jf_pt* Rq = &Bq[7];
-    jf_pt* Rh = &Bh8;
+    jf_pt* Rh = SB_BH(7);
     jf_pt* Oh = R;
     jf_pt Oq = Bq[7];
-    *Oh = Bh8;
+    *Oh = *Rh;
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
     // `same_h`: O_h and R_h are the same (finite) point.  It happens whenever the buckets below the highest used
     // digit magnitude are empty (~2e-4 of random challenges): O += R is then a doubling, taken on a divergent
