@@ -77,8 +77,8 @@ def w_per_batch_signature(n: int, msg_len: int, plan=None) -> float:
 
 
 # ---- executed by the shipped kernels (host-build counter; pinned by the CPU test named above) ------------------------
-W_EXECUTED_FAST_L8 = 338055       # k_verify_fast, 8-byte message: products of the (X, Y, w) path incl. 2 permutations
-W_EXECUTED_EXACT_L8 = 532446      # k_verify (exact Jacobian path)
+W_EXECUTED_FAST_L8 = 335892       # k_verify_fast, 8-byte message: products of the (X, Y, w) path incl. 2 permutations
+W_EXECUTED_EXACT_L8 = 529896      # k_verify (exact Jacobian path)
 W_EXECUTED_PER_PERMUTATION = 28000
 
 

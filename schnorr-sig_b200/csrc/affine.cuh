@@ -412,7 +412,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     Dp->Y = py;
     Dp->w = 1;
 #pragma unroll 1
-    for (int j = 0; j < 256; j++) {
+    for (int j = 0; j < SB_CHAIN_STEPS; j++) {
         if ((j & SB_CHAIN_SYNC_MASK) == 0) SB_PHASE_SYNC(1);
         int dq = SB_QWNAF(j);
         if (dq != 0) {  // warp-uniform
@@ -437,7 +437,7 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
             exc |= jf_add<true>(SB_BH(idx), Dp, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0));
             if (mag) h_seen |= 1u << idx;
         }
-        if (j < 255) exc |= jf_dbl<true>(Dp);
+        if (j < SB_CHAIN_STEPS - 1) exc |= jf_dbl<true>(Dp);
     }
     // Bucket aggregation (R_k = sum_{m>=k} B_m, O_k = sum_{m>=k} R_m):
     //   q (odd digits 2k+1):  [q]P = 2 O_1 + R_0        h (digits m = k+1):  h*P = O_0

@@ -206,6 +206,14 @@ __constant__ int8_t c_q_wnaf4[256];  // CHEETAH_Q_WNAF4, filled at context creat
 #ifndef SB_Q_NAF_W
 #define SB_Q_NAF_W 5  // measured: width 5 = 7.84 M/s, width 4 = 7.74 M/s (profiles/r1_variants.md)
 #endif
+// Steps of the shared doubling chain D_j = 2^j P: the last 4-bit window of the challenge starts at bit 252, and the
+// generated width-5 digits of q end at bit 251 (tools/gen_params.py: fold_top), so D_253..D_255 are never needed.
+#if SB_Q_NAF_W == 5
+static constexpr int SB_CHAIN_STEPS = 253;
+static_assert(CHEETAH_Q_WNAF5_LEN <= SB_CHAIN_STEPS, "digits of q above the last challenge window");
+#else
+static constexpr int SB_CHAIN_STEPS = 256;
+#endif
 #if SB_Q_NAF_W == 5
 #define SB_QNAF(i) SB_QWNAF(i)
 #elif defined(__CUDACC__)
@@ -261,7 +269,7 @@ SB_DEV void bucket_aggregate_odd(const jac_pt* B, int nb, jac_pt* out) {
     jac_add_mem(out, &running, false);
 }
 // returns [q]P == O (AffinePoint::is_torsion_free, src/signature.rs:182) and writes h*P.
-// One doubling chain D_j = 2^j P, j = 0..255.  q is consumed in its constant width-w NAF (non-zero odd
+// One doubling chain D_j = 2^j P, j = 0..SB_CHAIN_STEPS-1.  q is consumed in its constant width-w NAF (non-zero odd
 // digits at arbitrary bit positions -> 2^(w-2) buckets of odd multiples, warp-uniform control flow);
 // h in signed 4-bit windows at every fourth step (per-thread digits, uniform trip count).
 // `Dp` is caller-provided storage for the running point D_j (the kernels place it in shared memory: it is
@@ -276,7 +284,7 @@ SB_DEV bool torsion_check_and_mul(const jac_pt& P, const scalar& h, jac_pt* hP, 
     recode_signed_w4(h, hd);
     *Dp = P;
 #pragma unroll 1
-    for (int j = 0; j < 256; j++) {
+    for (int j = 0; j < SB_CHAIN_STEPS; j++) {
         if ((j & 3) == 0) SB_PHASE_SYNC(1);
         if (j != 0) jac_dbl_mem(Dp);
         int dq = SB_QNAF(j);

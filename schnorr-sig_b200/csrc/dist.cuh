@@ -250,7 +250,7 @@ __device__ int dverify_core(unsigned mask, fp_t px, fp_t py, const scalar& h, co
     }
     D = dpt{px, py, 1};
 #pragma unroll 1
-    for (int j = 0; j < 256; j++) {
+    for (int j = 0; j < SB_CHAIN_STEPS; j++) {
         if ((j & 3) == 0) SB_PHASE_SYNC(1);
         int dq = SB_QWNAF(j);
         if (dq != 0) {
@@ -270,7 +270,7 @@ __device__ int dverify_core(unsigned mask, fp_t px, fp_t py, const scalar& h, co
             exc |= djf_add(mask, &Bh[idx], &D, jf_add_mode(!((h_seen >> idx) & 1), mag == 0, dh < 0), k, gbase);
             if (mag) h_seen |= 1u << idx;
         }
-        if (j < 255) exc |= djf_dbl(mask, &D, k, gbase);
+        if (j < SB_CHAIN_STEPS - 1) exc |= djf_dbl(mask, &D, k, gbase);
     }
     dpt Rq = Bq[7], Oq = Bq[7], Rh = Bh[7], Oh = Bh[7];
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;

@@ -46,6 +46,32 @@ def wnaf(k, w):
     return out
 
 
+def fold_top(digits, w, top):
+    """Rewrite the two most significant digits of a width-w NAF so that no digit sits above bit `top`: the verification
+    kernels walk ONE doubling chain for the subgroup check and for the challenge product, whose last 4-bit window starts
+    at bit 252 -- a digit of q at bit 255 would cost three doublings nobody else needs.  The digit set (odd, |d| < 2^(w-1))
+    and the number of non-zero digits are unchanged; only the non-adjacency of the top pair is given up, which the bucket
+    method does not rely on."""
+    d = list(digits)
+    while len(d) - 1 > top:
+        nz = [i for i, x in enumerate(d) if x]
+        i1, i2 = nz[-2], nz[-1]
+        m = d[i1] + (d[i2] << (i2 - i1))
+        lim = 1 << (w - 1)
+        for s in range(1, top - i1 + 1):
+            cands = [(a, b) for b in range(-lim + 1, lim, 2) for a in [m - (b << s)] if a & 1 and abs(a) < lim]
+            if cands and not any(d[i1 + 1:i1 + s + 1]):
+                a, b = cands[0]
+                d[i1], d[i2] = a, 0
+                d[i1 + s] = b
+                break
+        else:
+            raise ValueError("cannot fold the top digits below bit %d" % top)
+        while d and d[-1] == 0:
+            d.pop()
+    return d
+
+
 def main():
     G = o.generator()
     ark = o.rescue_round_constants()
@@ -71,8 +97,9 @@ def main():
     q_inv32 = (-pow(Q, -1, 1 << 32)) % (1 << 32)
     r2 = (R * R) % Q
 
-    q_wnaf5 = wnaf(Q, 5)
-    assert sum(d << i for i, d in enumerate(q_wnaf5)) == Q
+    q_wnaf5 = fold_top(wnaf(Q, 5), 5, 251)
+    assert sum(d << i for i, d in enumerate(q_wnaf5)) == Q and len(q_wnaf5) == 252
+    assert all(d == 0 or (d & 1 and abs(d) < 16) for d in q_wnaf5) and sum(1 for d in q_wnaf5 if d) == 44
     q_wnaf4 = wnaf(Q, 4)
     assert sum(d << i for i, d in enumerate(q_wnaf4)) == Q and len(q_wnaf4) == 256
 
@@ -157,7 +184,7 @@ def main():
     h.append(arr64("CHEETAH_KAT_Y", list(o.KAT_Y)))
     h.append("/* width-5 NAF of q, least-significant digit first (uniform addition chain of the subgroup check) */\n")
     h.append("#define CHEETAH_Q_WNAF5_LEN %d\n" % len(q_wnaf5))
-    h.append(arr8("CHEETAH_Q_WNAF5", q_wnaf5))
+    h.append(arr8("CHEETAH_Q_WNAF5", q_wnaf5 + [0] * (256 - len(q_wnaf5))))   # zero-padded: the chain loops index up to 255
     h.append("/* width-4 NAF of q (digits +-1,3,5,7), least-significant digit first */\n")
     h.append(arr8("CHEETAH_Q_WNAF4", q_wnaf4))
     h.append("/* Frobenius: (u^i)^p = FP6_FROB[i] * u^i */\n")
