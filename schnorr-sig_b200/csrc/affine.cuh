@@ -189,6 +189,11 @@ SB_SCALE_FN fp6 fp6_scale_diff_nc(fp6 a, fp_t s, fp6 nb, fp_t t) {  // nb = a re
 // form: the fused helpers take 38 argument registers, which costs k_msm_segment_sum a resident block.
 template <bool FUSED = false>
 SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
+#if defined(__CUDA_ARCH__)
+    // The fused form is only ever handed a shared-memory slot (the running point of k_verify_fast): telling the compiler
+    // turns 26 generic accesses -- each with its own descriptor set-up (two R2UR) -- into LDS / STS.
+    if (FUSED) __builtin_assume(__isShared(p));
+#endif
     fp6 X = p->X, Y = p->Y, c;
     fp_t w = p->w, n;
     fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / (2 n)
@@ -446,7 +451,8 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
     jf_pt* Rq = &Bq[7];
     jf_pt* Rh = SB_BH(7);
     jf_pt* Oh = R;
-    jf_pt Oq = Bq[7];
+    jf_pt& Oq = *Dp;   // the chain is over: its slot (shared memory, what jf_dbl<true> expects) holds O_q from here on
+    Oq = Bq[7];
     *Oh = *Rh;
     bool eRq = !((q_seen >> 7) & 1), eOq = eRq, eRh = !((h_seen >> 7) & 1), eOh = eRh;
     // `same_h`: O_h and R_h are the same (finite) point.  It happens whenever the buckets below the highest used
@@ -468,7 +474,11 @@ SB_DEV int verify_core_fast(const fp6& px, const fp6& py, const scalar& h, const
         if (!eb && !eRh) same_h = false;  // a real addition changed R
         eRh = eRh && eb;
         if (__builtin_expect(same_h && !eOh, 0)) {
-            exc |= jf_dbl<true>(Oh);           // O == R: O + R = 2 O
+            jf_pt keep = Oq;                   // O == R: O + R = 2 O, doubled through the shared slot
+            Oq = *Oh;
+            exc |= jf_dbl<true>(&Oq);
+            *Oh = Oq;
+            Oq = keep;
             same_h = false;
         } else {
             exc |= jf_add<true>(Oh, Rh, jf_add_mode(eOh, eRh, false));
