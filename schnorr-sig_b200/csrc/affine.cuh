@@ -98,7 +98,15 @@ struct fp6_cof {
     fp6 c;
     fp_t n;
 };
-SB_DEV_NOINLINE fp6_cof fp6_cofactor_norm_v(fp6 d) {
+#ifndef SB_INL_COF
+#define SB_INL_COF 0
+#endif
+#if SB_INL_COF
+SB_DEV
+#else
+SB_DEV_NOINLINE
+#endif
+fp6_cof fp6_cofactor_norm_v(fp6 d) {
     fp6_cof out;
     fp6* c = &out.c;
     fp_t* n = &out.n;

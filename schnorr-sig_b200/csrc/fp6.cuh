@@ -156,31 +156,58 @@ SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
     return r;
 }
 #endif
-SB_DEV_NOINLINE fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
+// EXPERIMENT knobs: inline the two-call-site helpers of the fused point formulas as well (duplicates their code)
+#ifndef SB_INL_MSS
+#define SB_INL_MSS 0
+#endif
+#ifndef SB_INL_MULNC
+#define SB_INL_MULNC 0
+#endif
+#if SB_INL_MSS
+SB_DEV
+#else
+SB_DEV_NOINLINE
+#endif
+fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
     fp6 r;
     fp6_mul_sub_scaled_body(r, a, b, c, s);
     return r;
 }
 // a * b with non-canonical coefficients (feeds multiplications only)
-SB_DEV_NOINLINE fp6 fp6_mul_nc(fp6 a, fp6 b) {
+#if SB_INL_MULNC
+SB_DEV
+#else
+SB_DEV_NOINLINE
+#endif
+fp6 fp6_mul_nc(fp6 a, fp6 b) {
     fp6 r;
     fp6_mul_body<false>(r, a, b);
     return r;
 }
+// The three squaring forms below have ONE call site per kernel (the fused doubling / addition, the mixed addition of
+// the MSM): inlined there they cost no code and save the argument marshalling of a call (SB_SQR_INLINE, measured).
+#ifndef SB_SQR_INLINE
+#define SB_SQR_INLINE 1
+#endif
+#if SB_SQR_INLINE
+#define SB_SQR_FN SB_DEV
+#else
+#define SB_SQR_FN SB_DEV_NOINLINE
+#endif
 // a^2 with non-canonical coefficients
-SB_DEV_NOINLINE fp6 fp6_sqr_nc(fp6 a) {
+SB_SQR_FN fp6 fp6_sqr_nc(fp6 a) {
     fp6 r;
     fp6_sqr_body_t<0, false>(r, a, nullptr, nullptr, 0);
     return r;
 }
 // a^2 - 2 A
-SB_DEV_NOINLINE fp6 fp6_sqr_sub2(fp6 a, fp6 A) {
+SB_SQR_FN fp6 fp6_sqr_sub2(fp6 a, fp6 A) {
     fp6 r;
     fp6_sqr_body_t<1>(r, a, &A, nullptr, 0);
     return r;
 }
 // a^2 - A - B s
-SB_DEV_NOINLINE fp6 fp6_sqr_sub_scaled(fp6 a, fp6 A, fp6 B, fp_t s) {
+SB_SQR_FN fp6 fp6_sqr_sub_scaled(fp6 a, fp6 A, fp6 B, fp_t s) {
     fp6 r;
     fp6_sqr_body_t<2>(r, a, &A, &B, s);
     return r;
