@@ -98,15 +98,7 @@ struct fp6_cof {
     fp6 c;
     fp_t n;
 };
-#ifndef SB_INL_COF
-#define SB_INL_COF 0
-#endif
-#if SB_INL_COF
-SB_DEV
-#else
-SB_DEV_NOINLINE
-#endif
-fp6_cof fp6_cofactor_norm_v(fp6 d) {
+SB_DEV fp6_cof fp6_cofactor_norm_body(const fp6& d) {
     fp6_cof out;
     fp6* c = &out.c;
     fp_t* n = &out.n;
@@ -142,10 +134,24 @@ fp6_cof fp6_cofactor_norm_v(fp6 d) {
     *c = fp6_join(fp3_mul_pre(x, adj, adj7_1, adj7_2), fp3_mul_pre(ny, adj, adj7_1, adj7_2));
     return out;
 }
+SB_DEV_NOINLINE fp6_cof fp6_cofactor_norm_v(fp6 d) { return fp6_cofactor_norm_body(d); }
 SB_DEV void fp6_cofactor_norm(const fp6* d, fp6* c, fp_t* n) {
     fp6_cof r = fp6_cofactor_norm_v(*d);
     *c = r.c;
     *n = r.n;
+}
+// The slope of a chord / tangent up to its base-field denominator: L = num * (n / d), n = norm(d).  Cofactor and product
+// in ONE out-of-line function (the fused doubling and addition both end in this pair): the cofactor never leaves the
+// registers and one call with its argument marshalling is saved per point operation.  L not canonical.
+#ifndef SB_SLOPE_FUSED
+#define SB_SLOPE_FUSED 1
+#endif
+SB_DEV_NOINLINE fp6_cof fp6_slope_nc(fp6 num, fp6 d) {
+    fp6_cof r = fp6_cofactor_norm_body(d);
+    fp6 L;
+    fp6_mul_body<false>(L, num, r.c);
+    r.c = L;
+    return r;
 }
 
 // a * s for s in Fp (any 64-bit representative)
@@ -204,24 +210,31 @@ SB_DEV_NOINLINE bool jf_dbl(jf_pt* p) {
 #endif
     fp6 X = p->X, Y = p->Y, c;
     fp_t w = p->w, n;
-    fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / (2 n)
     if (FUSED) {
-        // slope = (3 X^2 + w^4) c / (2 n w) = (X^2 + w^4 / 3) c / (m w) with m = 2 n / 3: the factor 3 moves into the
-        // denominator (one product by a constant) instead of tripling the six coefficients of X^2
+        // slope = (3 X^2 + w^4) c / (2 n w) = (X^2 + w^4 / 3) c / (m w) with m = 2 n / 3 and 1 / (2 Y) = c / (2 n): the
+        // factor 3 moves into the denominator (one product by a constant) instead of tripling the six coefficients of X^2
         const fp_t inv3 = 0xaaaaaaaa00000001ULL, two_thirds = 0x5555555500000001ULL;
-        fp_t m = fp_mul(n, two_thirds);
         fp_t w4 = fp_mul(fp_sqr_nc(fp_sqr_nc(w)), inv3);
         fp6 num = fp6_sqr_nc(X);
         num.c[0] = fp_add(num.c[0], w4);    // (a non-canonical minuend is fine, fp_sub)
+#if SB_SLOPE_FUSED
+        fp6_cof sl = fp6_slope_nc(num, Y);
+        fp6 L = sl.c;                       // slope = L / (m w)
+        n = sl.n;
+#else
+        fp6_cofactor_norm(&Y, &c, &n);
+        fp6 L = fp6_mul_nc(num, c);
+#endif
+        fp_t m = fp_mul(n, two_thirds);
         fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
         fp6 A = fp6_scale(X, m2);
-        fp6 L = fp6_mul_nc(num, c);         // slope = L / (m w)
         fp6 X3 = fp6_sqr_sub2(L, A);
         p->Y = fp6_mul_sub_scaled(L, fp6_sub(A, X3), Y, m3);
         p->X = X3;
         p->w = fp_mul(m, w);
         return n == 0;
     }
+    fp6_cofactor_norm(&Y, &c, &n);          // 1 / (2 Y) = c / (2 n)
     fp_t m = fp_add(n, n);
     fp_t w4 = fp_sqr(fp_sqr_nc(w));
     fp6 xx = fp6_sqr(X);
@@ -269,8 +282,14 @@ SB_DEV_NOINLINE bool jf_add(jf_pt* acc, const jf_pt* src, uint8_t mode) {
 #pragma unroll
         for (int i = 0; i < 6; i++) nY2.c[i] = negate ? Y2.c[i] : FP_P - Y2.c[i];
         fp6 num = fp6_scale_diff_nc(Y1, w2c, nY2, w1c);
+#if SB_SLOPE_FUSED
+        fp6_cof sl = fp6_slope_nc(num, d);
+        fp6 L = sl.c;                                // slope = L / (n w1 w2)
+        n = sl.n;
+#else
         fp6_cofactor_norm(&d, &c, &n);
-        fp6 L = fp6_mul_nc(num, c);                  // slope = L / (n w1 w2)
+        fp6 L = fp6_mul_nc(num, c);
+#endif
         fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
         fp6 A = fp6_scale(X1, fp_mul_nc(n2, w2s));   // n^2 U1 = x1 w3^2
         fp6 X3 = fp6_sqr_sub_scaled(L, A, X2, fp_mul_nc(n2, w1s));            // L^2 - x1 w3^2 - x2 w3^2
@@ -326,10 +345,16 @@ SB_DEV_NOINLINE bool jf_madd(jf_pt* acc, const jf_pt* t, bool neg) {
         wide_mac(w, neg ? Y2.c[i] : FP_P - Y2.c[i], w1c);
         num.c[i] = wide_reduce_nc(w);
     }
-    fp6 c;
     fp_t n;
+#if SB_SLOPE_FUSED
+    fp6_cof sl = fp6_slope_nc(num, d);
+    fp6 L = sl.c;                                     // slope = L / (n w1)
+    n = sl.n;
+#else
+    fp6 c;
     fp6_cofactor_norm(&d, &c, &n);
-    fp6 L = fp6_mul_nc(num, c);                       // slope = L / (n w1)
+    fp6 L = fp6_mul_nc(num, c);
+#endif
     fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
     fp6 A = fp6_scale(X1, n2);                        // x1 w3^2
     fp6 X3 = fp6_sqr_sub_scaled(L, A, X2, fp_mul_nc(n2, w1s));
