@@ -202,6 +202,22 @@ def test_params_json_matches_oracle():
     assert pj["rescue"]["rounds"] == o.RESCUE_ROUNDS
 
 
+def test_generated_subgroup_check_digits_represent_q():
+    """The kernels' subgroup check consumes q through the generated digit table (include/cheetah_params.h:
+    CHEETAH_Q_WNAF5): it must represent q exactly, with odd digits below 16 (eight buckets), and stop below bit 252 --
+    the shared doubling chain of the verification ends with the last challenge window (tools/gen_params.py: fold_top)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "cheetah_params.h")).read()
+    body = re.search(r"CHEETAH_Q_WNAF5\[(\d+)\] = \{(.*?)\};", text, re.S)
+    digits = [int(t) for t in body.group(2).replace("\n", " ").split(",") if t.strip()]
+    assert len(digits) == int(body.group(1)) == 256
+    assert sum(d << i for i, d in enumerate(digits)) == o.Q
+    assert all(d == 0 or (d % 2 == 1 and abs(d) < 16) for d in digits)
+    top = max(i for i, d in enumerate(digits) if d)
+    assert top <= 251 and int(re.search(r"#define CHEETAH_Q_WNAF5_LEN (\d+)", text).group(1)) == top + 1
+    assert sum(1 for d in digits if d) == 44
+
+
 def test_upstream_dump_known_answers_when_present():
     """rust/dump_params (run on a machine with cargo + network) writes params/upstream_dump.json from the REAL cheetah /
     hash crates.  Absent here -> the oracle stays "parity unpinned" at value level (DESIGN.md 3) and this test SKIPS;
