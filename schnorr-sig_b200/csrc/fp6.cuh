@@ -156,30 +156,15 @@ SB_DEV_NOINLINE fp6 fp6_sqr(fp6 a) {
     return r;
 }
 #endif
-// EXPERIMENT knobs: inline the two-call-site helpers of the fused point formulas as well (duplicates their code)
-#ifndef SB_INL_MSS
-#define SB_INL_MSS 0
-#endif
-#ifndef SB_INL_MULNC
-#define SB_INL_MULNC 0
-#endif
-#if SB_INL_MSS
-SB_DEV
-#else
-SB_DEV_NOINLINE
-#endif
-fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
+// (helpers with TWO call sites per kernel stay out of line: duplicating them costs what the calls save,
+// profiles/r2_variants.md)
+SB_DEV_NOINLINE fp6 fp6_mul_sub_scaled(fp6 a, fp6 b, fp6 c, fp_t s) {
     fp6 r;
     fp6_mul_sub_scaled_body(r, a, b, c, s);
     return r;
 }
 // a * b with non-canonical coefficients (feeds multiplications only)
-#if SB_INL_MULNC
-SB_DEV
-#else
-SB_DEV_NOINLINE
-#endif
-fp6 fp6_mul_nc(fp6 a, fp6 b) {
+SB_DEV_NOINLINE fp6 fp6_mul_nc(fp6 a, fp6 b) {
     fp6 r;
     fp6_mul_body<false>(r, a, b);
     return r;

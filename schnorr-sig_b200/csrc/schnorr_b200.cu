@@ -276,11 +276,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_verify(so
 #ifndef VERIFY_FAST_MIN_BLOCKS
 #define VERIFY_FAST_MIN_BLOCKS 2
 #endif
-#ifdef SB_FAST_D_LOCAL
-static constexpr size_t VERIFY_FAST_SMEM = (size_t)FAST_BH_SHARED * VERIFY_THREADS * sizeof(jf_pt);
-#else
-static constexpr size_t VERIFY_FAST_SMEM = (size_t)(1 + FAST_BH_SHARED) * VERIFY_THREADS * sizeof(jf_pt);
-#endif  // 106 496 B: two blocks per SM
+static constexpr size_t VERIFY_FAST_SMEM = (size_t)(1 + FAST_BH_SHARED) * VERIFY_THREADS * sizeof(jf_pt);  // 106 496 B: two blocks per SM
 __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_verify_fast(soa_batch in, const uint8_t* __restrict__ msgs,
                                                            const uint64_t* __restrict__ msg_off,
                                                            const uint64_t* __restrict__ gtab,
@@ -291,13 +287,8 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
     // challenge buckets per thread, bucket-major.  A slot is 104 bytes: 64-bit accesses of a half-warp fall into sixteen
     // distinct even banks whatever bucket each thread addresses.
     extern __shared__ __align__(16) unsigned char s_fast[];
-#ifdef SB_FAST_D_LOCAL
-    jf_pt d_local;
-    jf_pt* s_bh = reinterpret_cast<jf_pt*>(s_fast);
-#else
     jf_pt* s_d = reinterpret_cast<jf_pt*>(s_fast);
     jf_pt* s_bh = s_d + VERIFY_THREADS;
-#endif
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < in.n;
     uint8_t fl = live ? in.flags[i] : FL_MALFORMED;
@@ -329,13 +320,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_FAST_MIN_BLOCKS) k_veri
         h = challenge_scalar(sx, px, py, false, msgs + off, len, hv.sync);
         if (!x_ok || !work) h = sc_zero();
     }
-    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, false, h, gtab,
-#ifdef SB_FAST_D_LOCAL
-                                   &d_local,
-#else
-                                   s_d + threadIdx.x,
-#endif
-                                   s_bh + threadIdx.x, VERIFY_THREADS);
+    uint8_t v = verify_points_fast(sx, x_ok, e, px, py, false, h, gtab, s_d + threadIdx.x, s_bh + threadIdx.x, VERIFY_THREADS);
     if (!live) return;
     if (fl & FL_MALFORMED) v = VERDICT_MALFORMED;
     else if (fl & FL_PK_INF) v = VERDICT_NEEDS_EXACT;   // the identity key is the exact kernel's business
