@@ -61,22 +61,19 @@ static int multi_run(schnorr_b200_ctx* ctx, const std::vector<shard_slice>& sl, 
 
 static int multi_verify_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs81, const uint8_t* pk96, const uint8_t* pk_inf,
                              const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts) {
-    if (n && msg_off[0] != 0) {
+    auto sl = multi_slices(ctx, n);
+    // the hot entry point: every shard gets its slice of the caller's offset table as it is (no rebasing pass) and
+    // validates it chunk by chunk inside its own pipeline, on its own host thread; here only the slice boundaries are
+    // checked, which bounds every shard's view of the blob by msg_off[n]
+    bool ok = n == 0 || msg_off[0] == 0;
+    for (const shard_slice& s : sl) ok = ok && msg_off[s.lo] <= msg_off[s.hi] && msg_off[s.hi] <= msg_off[n];
+    if (!ok) {
         ctx->err = "message offsets must start at 0 and be non-decreasing";
         return SCHNORR_B200_EARG;
     }
-    auto sl = multi_slices(ctx, n);
-    // the hot entry point: every shard gets its slice of the caller's offset table as it is and validates that slice on
-    // its own host thread (a single pass over 8 x 2^20 offsets on the calling thread costs ~10 ms of an 84 ms step); no
-    // per-shard rebasing pass either
     return multi_run(ctx, sl, [&](int k, shard_slice s) {
-        for (size_t i = s.lo; i < s.hi; i++)
-            if (msg_off[i + 1] < msg_off[i]) {
-                ctx->shards[k]->err = "message offsets must start at 0 and be non-decreasing";
-                return (int)SCHNORR_B200_EARG;
-            }
         return verify_many_host(ctx->shards[k], s.hi - s.lo, sigs81 + 81 * s.lo, pk96 + 96 * s.lo,
-                                pk_inf ? pk_inf + s.lo : nullptr, msgs, msg_off + s.lo, verdicts + s.lo);
+                                pk_inf ? pk_inf + s.lo : nullptr, msgs, msg_off + s.lo, verdicts + s.lo, true);
     });
 }
 static int multi_verify_keyed_many(schnorr_b200_ctx* ctx, size_t n, const uint8_t* keyed130, const uint8_t* msgs,

@@ -136,6 +136,36 @@ def test_pipelined_chunks_with_adversarial_keys_on_the_boundaries():
     assert {0, 1, 3} <= set(int(v) for v in np.unique(want))
 
 
+@pytest.mark.parametrize("devices", [None, 2])
+def test_offset_table_that_goes_bad_in_a_late_chunk_is_refused(devices):
+    """The C ABI validates the message offsets chunk by chunk inside the pipeline (behind the kernels of the chunks
+    before): a table that decreases, or runs past its last entry, anywhere -- first chunk, last chunk, a shard of a
+    multi-device context -- ends the call with EARG, never with an out-of-range read, and the context stays usable."""
+    s, eng0 = _engine()
+    eng = eng0 if devices is None else s.Engine(_device_list(devices))
+    wave = 148 * 2 * 128
+    n = 4 * wave + 1000
+    w = s.synth.signed_workload(eng0, 0xBAD0, n, msg_len=8)
+    sigs, pk, inf, blob = w["sigs"], w["pk"], w["inf"], w["blob"]
+    good = np.ascontiguousarray(w["off"], dtype=np.uint64)
+    out = np.full(n, 255, dtype=np.uint8)
+    for where in (5, wave + 7, n - 3):
+        for kind in ("decreasing", "beyond_the_end"):
+            off = good.copy()
+            if kind == "decreasing":
+                off[where] = off[where - 1] - 1 if off[where - 1] else off[where + 1] + 1
+            else:
+                off[where] = off[-1] + 64   # non-decreasing up to here, then back down: also caught as a decrease
+            with pytest.raises(s.EngineError, match="non-decreasing"):
+                eng.verify_many_raw(n, sigs, pk, inf, blob, off, out)
+    off = good.copy()
+    off[0] = 1
+    with pytest.raises(s.EngineError, match="non-decreasing"):
+        eng.verify_many_raw(n, sigs, pk, inf, blob, off, out)
+    eng.verify_many_raw(n, sigs, pk, inf, blob, good, out)       # and the context still works
+    assert int(out.max()) == 0
+
+
 def _device_list(want):
     import torch
     c = torch.cuda.device_count()
