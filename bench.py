@@ -613,7 +613,7 @@ def side_measurements(args, eng, stream, dev, torch, n, d_sigs, d_pk, d_inf, d_b
                 eng.verify_many(sig_s, pk_s, inf_s, blob_s, off_s)
                 ts.append(time.perf_counter() - t0)
             small_calls["n%d_ms" % ns_] = float(np.mean(ts)) * 1e3
-        small_calls["kernel"] = "k_verify_dist (one signature per six lanes)"
+        small_calls["kernel"] = "n1: k_verify_one (one thread block per signature); n1024: k_verify_dist (one signature per six lanes)"
         out["small_calls"] = small_calls
         out["criterion_protocol"] = criterion_protocol(eng, sb)
         out["hash_sweep"] = hash_sweep(eng, torch, dev, stream, peak_w)

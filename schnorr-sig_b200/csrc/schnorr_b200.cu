@@ -53,6 +53,7 @@ struct schnorr_b200_ctx {
     int last_msm_c = 0, last_msm_K = 0;             // Pippenger geometry of the last batch call (schnorr_b200_last_batch_plan)
     uint32_t last_msm_T = 0;
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
+    size_t one_max = 512;                           // ... and up to this many the block-per-signature kernel (one.cuh)
     size_t batch_dist_max = (size_t)1 << 18;        // batches up to this size hash their challenges on six lanes per signature
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
@@ -380,6 +381,9 @@ __global__ void __launch_bounds__(DIST_THREADS) k_verify_dist(soa_batch in, cons
         if (v == VERDICT_NEEDS_EXACT) work_list[atomicAdd(work_count, 1u)] = (uint32_t)i;
     }
 }
+
+// K2 for the smallest calls: one thread block per signature (needs soa_batch and the ingest flags defined above)
+#include "one.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K1: hash_message, one message per thread (AoS inputs: 8-byte aligned records)
@@ -800,7 +804,9 @@ static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint
     uint32_t* list = counters + schnorr_b200_ctx::MAX_CHUNKS + list_base;
     CUDA_TRY(ctx, cudaMemsetAsync(counters + counter, 0, 4, st));
     if (counter + 1 > ctx->exact_counters_used) ctx->exact_counters_used = counter + 1;
-    if (soa.n <= ctx->dist_max)
+    if (soa.n <= ctx->one_max)
+        k_verify_one<<<(unsigned)soa.n, ONE_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+    else if (soa.n <= ctx->dist_max)
         k_verify_dist<<<grid_for(soa.n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list,
                                                                                    counters + counter);
     else
@@ -985,6 +991,12 @@ int schnorr_b200_set_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures
     if (!ctx) return SCHNORR_B200_EARG;
     for (schnorr_b200_ctx* sh : ctx->shards) sh->dist_max = max_signatures;
     ctx->dist_max = max_signatures;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_set_one_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    for (schnorr_b200_ctx* sh : ctx->shards) sh->one_max = max_signatures;
+    ctx->one_max = max_signatures;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_set_batch_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {

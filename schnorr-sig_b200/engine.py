@@ -114,6 +114,10 @@ class Engine:
         """Calls up to this many signatures use the six-lanes-per-signature kernel (0 = never, 2**62 = always)."""
         self._check(self._L.schnorr_b200_set_dist_threshold(self._h, int(max_signatures)), "set_dist_threshold")
 
+    def set_one_threshold(self, max_signatures: int):
+        """Calls up to this many signatures use the block-per-signature kernel (0 = never)."""
+        self._check(self._L.schnorr_b200_set_one_threshold(self._h, int(max_signatures)), "set_one_threshold")
+
     def set_batch_dist_threshold(self, max_signatures: int):
         """Batches up to this size hash their challenges on six lanes per signature (0 = never)."""
         self._check(self._L.schnorr_b200_set_batch_dist_threshold(self._h, int(max_signatures)), "set_batch_dist_threshold")

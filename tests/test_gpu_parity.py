@@ -166,6 +166,51 @@ def test_affine_fast_path_agrees_with_exact_kernel_and_hands_back_exceptional_it
         assert 3 <= handed_back[name] <= 3 + n // 100, (name, handed_back)
 
 
+ONE_DEFAULT = 512   # schnorr_b200_set_one_threshold default (include/schnorr_b200.h)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 21, 64, 700])
+def test_block_per_signature_kernel_matches_oracle(eng, n):
+    """k_verify_one (one thread block per signature, one.cuh: doubling chain, challenge, e*G and the sixteen bucket
+    accumulations side by side) forced for every size: ragged messages incl. empty ones, injected faults, small-order /
+    mixed-order / identity keys, malformed records -> the oracle's verdicts, and the same verdicts as the six-lane and the
+    per-thread kernels."""
+    import schnorr_sig_b200 as s
+    rng = np.random.default_rng(1900 + n)
+    lens = [int(x) for x in rng.integers(0, 60, n)]
+    lens[:min(n, 8)] = [8, 0, 1, 6, 7, 13, 14, 49][:min(n, 8)]
+    w = make_workload(1900 + n, n, lens=lens)
+    w["n"], w["msg_len"] = n, 1
+    f = s.synth.inject_faults(w, every=7) if n >= 7 else dict(w, expect=np.zeros(n, np.uint8))
+    adversarial = 0
+    if n >= 21:
+        kat = (o.KAT_X, o.KAT_Y)
+        order = o.COFACTOR * o.Q
+        f["pk"][2] = pt_to96(o.pt_mul(kat, order // 2))      # order 2
+        f["pk"][9] = pt_to96(o.pt_mul(kat, order // 29))     # order 29: P + P / P - P inside the buckets
+        f["pk"][10] = pt_to96(o.pt_add(o.generator(), o.pt_mul(kat, order // 2)))   # order 2q
+        f["pk"][12] = KAT96                                    # the reference's off-subgroup point -> InvalidPublicKey
+        f["inf"][11] = 1                                     # identity key
+        f["sigs"][13, 8:16] = 0xFF                           # non-canonical sig.x limb
+        f["sigs"][15, 49:] = 0xFF                            # e >= q
+        adversarial = 4
+    want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
+    eng.set_one_threshold(2**62)
+    try:
+        got = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
+        handed_back = eng.last_exact_count()
+    finally:
+        eng.set_one_threshold(ONE_DEFAULT)
+    assert np.array_equal(got, want)
+    assert not (got == 0xFF).any()
+    assert handed_back <= adversarial
+    eng.set_one_threshold(0)
+    try:
+        assert np.array_equal(eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"]), want)
+    finally:
+        eng.set_one_threshold(ONE_DEFAULT)
+
+
 @pytest.mark.parametrize("n", [1, 4, 5, 6, 21, 127, 1000])
 def test_warp_cooperative_kernel_matches_oracle(eng, n):
     """k_verify_dist (one signature per six lanes, dist.cuh) forced for every size: ragged messages (different hash
@@ -187,18 +232,22 @@ def test_warp_cooperative_kernel_matches_oracle(eng, n):
         f["sigs"][15, 49:] = 0xFF             # e >= q
     want = cref.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"], cref.default_threads())
     eng.set_dist_threshold(2**62)
+    eng.set_one_threshold(0)              # (small calls would otherwise take the block-per-signature kernel)
     try:
         got = eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"])
         handed_back = eng.last_exact_count()
     finally:
         eng.set_dist_threshold(10240)
+        eng.set_one_threshold(ONE_DEFAULT)
     assert np.array_equal(got, want)
     assert handed_back <= (3 if n >= 21 else 0)
     eng.set_dist_threshold(0)
+    eng.set_one_threshold(0)              # one signature per thread for every size
     try:
         assert np.array_equal(eng.verify_many(f["sigs"], f["pk"], f["inf"], f["blob"], f["off"]), want)
     finally:
         eng.set_dist_threshold(10240)
+        eng.set_one_threshold(ONE_DEFAULT)
 
 
 def test_verify_empty_and_argument_errors(eng):
