@@ -5,8 +5,9 @@
 // ~100 bucket additions, 27 additions of bucket aggregation, 20 table additions -- 0.93 ms however idle the GPU is.  Most
 // of that chain is not a true dependency: only the doublings D_j = 2^j P depend on each other.  Here the four warps of a
 // block split the work of ONE signature in three barrier-separated phases (same arithmetic, same six-lane primitives):
-//   A  warp 0: the doubling chain, every D_j stored to shared memory (253 x 104 B);   warp 1: the challenge hash and its
-//      signed digits;   warp 2: e*G from the fixed-base table  -- side by side
+//   A  warp 0: the doubling chain, every D_j stored to shared memory (253 x 104 B), with warp 3 computing the one product
+//      of a doubling that does not depend on the cofactor (X^2);   warp 1: the challenge hash and its signed digits;
+//      warp 2: e*G from the fixed-base table  -- side by side
 //   B  the sixteen bucket accumulations (eight of the subgroup check, eight of the challenge) on sixteen six-lane groups
 //      at once, each group adding the chain points of ITS bucket (a compacted list, so a warp's groups stay in step)
 //   C  warp 0: aggregation of the subgroup-check buckets and the [q]P == O test;   warp 1: aggregation of the challenge
@@ -26,6 +27,7 @@ struct one_shared {
     fp_t cx[SB_CHAIN_STEPS][6], cy[SB_CHAIN_STEPS][6], cw[SB_CHAIN_STEPS];  // the chain D_j
     fp_t bx[ONE_SLOTS][6], by[ONE_SLOTS][6], bw[ONE_SLOTS];                 // bucket sums
     fp_t ex[6], ey[6], ew;                                                  // e*G
+    fp_t xx[6];                                                             // X^2 of the current chain point (helper warp)
     uint32_t mds2[24];
     int8_t hd[64];                          // signed 4-bit digits of the challenge
     uint8_t lst[ONE_SLOTS][64];             // per bucket: chain steps to add (bit 7 of neg[] separately: steps reach 252)
@@ -72,18 +74,52 @@ __global__ void __launch_bounds__(ONE_THREADS) k_verify_one(soa_batch in, const 
     fp_t py = pl[((size_t)(8 + (k >> 1)) * n + i) * 2 + (k & 1)];
     bool exc = false;
 
-    // ---- phase A: doubling chain | challenge | e*G ------------------------------------------------------------------
-    if (g == 0) {
-        if (warp == 0) {
-            dpt D{px, py, 1};
+    // ---- phase A: doubling chain (+ helper) | challenge | e*G -------------------------------------------------------
+    // The chain is the critical path of the whole kernel.  Inside one doubling only X^2 is independent of the
+    // cofactor of Y: warp 3 computes it while warp 0 works on the cofactor (two named barriers per step between the 64
+    // threads of the two warps; jf_dbl of affine.cuh / djf_dbl of dist.cuh otherwise).
+    if (warp == 0 || warp == 3) {
+        dpt D{px, py, 1};
 #pragma unroll 1
-            for (int j = 0; j < SB_CHAIN_STEPS; j++) {
+        for (int j = 0; j < SB_CHAIN_STEPS - 1; j++) {
+            fp_t c = 0, nrm = 0;
+            if (warp == 0 && g == 0) {
                 S.cx[j][k] = D.X;
                 S.cy[j][k] = D.Y;
                 if (k == 0) S.cw[j] = D.w;
-                if (j < SB_CHAIN_STEPS - 1) exc |= djf_dbl(mask, &D, k, gbase);
             }
-        } else if (warp == 1) {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (g == 0) {
+                if (warp == 3) S.xx[k] = dfp6_mul(mask, S.cx[j][k], S.cx[j][k], k, gbase);
+                else c = dfp6_cofactor_norm(mask, D.Y, k, gbase, &nrm);   // 1 / (2 Y) = c / (2 n)
+            }
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            if (warp == 0 && g == 0) {
+                fp_t X = D.X, Y = D.Y, w = D.w;
+                fp_t m = fp_add(nrm, nrm);
+                fp_t w4 = fp_sqr(fp_sqr_nc(w));
+                fp_t xx = S.xx[k];
+                fp_t num = fp_add(fp_dbl(xx), xx);
+                num = fp_add(num, k == 0 ? w4 : 0);                     // 3 X^2 + a w^4, a = 1
+                fp_t L = dfp6_mul(mask, num, c, k, gbase);              // slope = L / (m w)
+                fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
+                fp_t A = fp_mul(X, m2);
+                fp_t X3 = fp_sub(fp_sub(dfp6_mul(mask, L, L, k, gbase), A), A);
+                fp_t Y3 = fp_sub(dfp6_mul(mask, L, fp_sub(A, X3), k, gbase), fp_mul(Y, m3));
+                D.X = X3;
+                D.Y = Y3;
+                D.w = fp_mul(m, w);
+                exc |= nrm == 0;                                        // a point of order 2
+            }
+        }
+        if (warp == 0 && g == 0) {
+            S.cx[SB_CHAIN_STEPS - 1][k] = D.X;
+            S.cy[SB_CHAIN_STEPS - 1][k] = D.Y;
+            if (k == 0) S.cw[SB_CHAIN_STEPS - 1] = D.w;
+        }
+    }
+    if (g == 0) {
+        if (warp == 1) {
             scalar h = sc_zero();
             uint64_t off = msg_off[i];
             if (x_ok) h = dchallenge_scalar(mask, sx, px, py, msgs + off, msg_off[i + 1] - off, k, gbase, S.mds2);
