@@ -91,10 +91,10 @@ int schnorr_b200_last_exact_count(schnorr_b200_ctx *ctx, uint64_t *count);
  * thread kernel.  0 disables it, SIZE_MAX forces it (tests).  Default 10240 (measured crossover ~12 k). */
 int schnorr_b200_set_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
 /* Calls of at most `max_signatures` signatures (per pipeline chunk) run one thread BLOCK per signature: the doubling
- * chain, the challenge hash, e*G and the sixteen bucket accumulations of one verification proceed side by side on the
- * block's warps (lowest latency for the reference's own Criterion case, a single Signature::verify,
- * benches/schnorr.rs:22-66).  0 disables it.  Default 512 (measured: 0.62-0.71 ms for 1..512 signatures against 1.03-1.07 ms on six lanes; beyond
- * ~1000 blocks the six-lane kernel is faster). */
+ * chain, the challenge hash, e*G and then the sixteen bucket accumulations of one verification proceed side by side on
+ * the block's warps (lowest latency for the reference's own Criterion case, a single Signature::verify,
+ * benches/schnorr.rs:22-66).  0 disables it.  Default 512 (measured: 0.50-0.65 ms for 1..512 signatures against
+ * 0.98-1.08 ms on six lanes; beyond ~1000 blocks the six-lane kernel is faster). */
 int schnorr_b200_set_one_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
 /* Batches of at most `max_signatures` compute their challenges with one signature per six lanes ahead of the (then
  * hash-free) prepare kernel; larger ones hash one signature per thread.  Default 2^18 (measured crossover). */

@@ -38,6 +38,13 @@ static msm_plan msm_make_plan(size_t npoints, int c_override = 0) {
             p.B = 1 << (c - 1);
         }
     }
+    // Small batches are latency-bound (one launch chain, the Horner tail is serial): 8-bit windows -- 32 Horner additions
+    // instead of the 52-64 of the work-optimal 4-5 bits -- measured best for 4..4096 signatures (tools/small_batch_c_scan.py)
+    if (npoints <= 8192) {
+        p.c = 8;
+        p.K = 32;
+        p.B = 128;
+    }
     if (c_override >= 4 && c_override <= 16) {  // schnorr_b200_set_msm_geometry (tests): force the window width
         p.c = c_override;
         p.K = (256 + p.c - 1) / p.c;

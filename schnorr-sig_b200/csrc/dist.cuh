@@ -18,17 +18,10 @@
 
 namespace sb {
 
-// FULL = true: every lane of the warp executes the call in lockstep (the groups replicate or run side by side, lanes 30
-// and 31 tag along), so the shuffles name the whole warp -- a plain SHFL.  With a partial, run-time mask every shuffle is
-// wrapped in a convergence barrier of its own (BSSY / WARPSYNC.COLLECTIVE / ... / BSYNC: six instructions and a
-// synchronisation per shuffle, 24 of them per Fp6 product), which is what the latency-bound single-warp chains
-// (k_verify_one, the Horner tail of the MSM) spend a third of their time on.
-template <bool FULL = false>
-__device__ __forceinline__ fp_t dshfl(unsigned mask, fp_t v, int src) { return __shfl_sync(FULL ? 0xffffffffu : mask, v, src); }
+__device__ __forceinline__ fp_t dshfl(unsigned mask, fp_t v, int src) { return __shfl_sync(mask, v, src); }
 
 // coefficient k of a * b in Fp6; a, b = the lane's coefficients of the two operands.  Step i: lane k needs a_i and
 // b'_(k - i mod 6); the source lane j is read by lane (j + i) mod 6, which wraps (needs 7 b_j) iff j + i >= 6.
-template <bool FULL = false>
 __device__ __noinline__ fp_t dfp6_mul(unsigned mask, fp_t a, fp_t b, int k, int gbase) {
     fp_t b7 = fp_mul7_nc(b);
     wide_acc w;
@@ -38,13 +31,12 @@ __device__ __noinline__ fp_t dfp6_mul(unsigned mask, fp_t a, fp_t b, int k, int 
         fp_t send = (k + i >= 6) ? b7 : b;
         int j = k - i;
         j += j < 0 ? 6 : 0;
-        wide_mac(w, dshfl<FULL>(mask, a, gbase + i), dshfl<FULL>(mask, send, gbase + j));
+        wide_mac(w, dshfl(mask, a, gbase + i), dshfl(mask, send, gbase + j));
     }
     return wide_reduce(w);
 }
 // Fp3 = Fp[v]/(v^3 - 7) products on the two 3-lane halves of a group at once: lanes of parity `par` hold the
 // coefficients t = k >> 1 of one Fp3 operand pair (even lanes: the c0,c2,c4 part of an Fp6 value, odd: c1,c3,c5)
-template <bool FULL = false>
 __device__ __noinline__ fp_t dfp3_mul(unsigned mask, fp_t a, fp_t b, int k, int gbase) {
     int par = k & 1, t = k >> 1;
     fp_t b7 = fp_mul7_nc(b);
@@ -55,27 +47,25 @@ __device__ __noinline__ fp_t dfp3_mul(unsigned mask, fp_t a, fp_t b, int k, int 
         fp_t send = (t + i >= 3) ? b7 : b;
         int j = t - i;
         j += j < 0 ? 3 : 0;
-        wide_mac(w, dshfl<FULL>(mask, a, gbase + 2 * i + par), dshfl<FULL>(mask, send, gbase + 2 * j + par));
+        wide_mac(w, dshfl(mask, a, gbase + 2 * i + par), dshfl(mask, send, gbase + 2 * j + par));
     }
     return wide_reduce(w);
 }
-template <bool FULL = false>
 __device__ __forceinline__ bool dall(unsigned mask, int gbase, bool v) {
-    return ((__ballot_sync(FULL ? 0xffffffffu : mask, v) >> gbase) & 0x3fu) == 0x3fu;
+    return ((__ballot_sync(mask, v) >> gbase) & 0x3fu) == 0x3fu;
 }
 
 // d * c = n (fp6_cofactor_norm of affine.cuh): e = the lane's coefficient of d; returns the lane's coefficient of c
 // and the norm n (replicated)
-template <bool FULL = false>
 __device__ __noinline__ fp_t dfp6_cofactor_norm(unsigned mask, fp_t e, int k, int gbase, fp_t* n_out) {
     int par = k & 1, t = k >> 1;
-    fp_t s = dfp3_mul<FULL>(mask, e, e, k, gbase);  // even lanes: (a0^2)_t, odd lanes: (a1^2)_t
+    fp_t s = dfp3_mul(mask, e, e, k, gbase);  // even lanes: (a0^2)_t, odd lanes: (a1^2)_t
     // N = a0^2 - v a1^2,  (v x)_t = x_(t-1), times 7 for t = 0; computed by both halves (replicated)
     int tm = t == 0 ? 2 : t - 1;
-    fp_t s0 = dshfl<FULL>(mask, s, gbase + 2 * t), s1 = dshfl<FULL>(mask, s, gbase + 2 * tm + 1);
+    fp_t s0 = dshfl(mask, s, gbase + 2 * t), s1 = dshfl(mask, s, gbase + 2 * tm + 1);
     fp_t s1_7 = fp_mul7(s1);
     fp_t N = fp_sub(s0, t == 0 ? s1_7 : s1);
-    fp_t d0 = dshfl<FULL>(mask, N, gbase), d1 = dshfl<FULL>(mask, N, gbase + 2), d2 = dshfl<FULL>(mask, N, gbase + 4);
+    fp_t d0 = dshfl(mask, N, gbase), d1 = dshfl(mask, N, gbase + 2), d2 = dshfl(mask, N, gbase + 4);
     fp_t d1_7 = fp_mul7_nc(d1), d2_7 = fp_mul7_nc(d2);
     // adjugate: t0 = d0^2 - 7 d1 d2,  t1 = 7 d2^2 - d0 d1,  t2 = d1^2 - d0 d2   (operands picked by selects)
     fp_t x = t == 0 ? d0 : (t == 1 ? d2 : d1);
@@ -87,14 +77,14 @@ __device__ __noinline__ fp_t dfp6_cofactor_norm(unsigned mask, fp_t e, int k, in
     wide_mac(w, x, xp);
     wide_mac(w, y, yp);
     fp_t adj = wide_reduce(w);
-    fp_t a0 = dshfl<FULL>(mask, adj, gbase), a1 = dshfl<FULL>(mask, adj, gbase + 2), a2 = dshfl<FULL>(mask, adj, gbase + 4);
+    fp_t a0 = dshfl(mask, adj, gbase), a1 = dshfl(mask, adj, gbase + 2), a2 = dshfl(mask, adj, gbase + 4);
     wide_zero(w);
     wide_mac(w, d0, a0);
     wide_mac(w, d2_7, a1);
     wide_mac(w, d1_7, a2);
     *n_out = wide_reduce(w);
     // c = (a0 - a1 u) * adj
-    fp_t r = dfp3_mul<FULL>(mask, e, adj, k, gbase);
+    fp_t r = dfp3_mul(mask, e, adj, k, gbase);
     return par ? fp_neg(r) : r;
 }
 
@@ -103,20 +93,19 @@ struct dpt {  // the lane's coefficients of X and Y; w (in Fp) replicated
 };
 
 // p <- 2 p (jf_dbl of affine.cuh); returns true on a 2-torsion point
-template <bool FULL = false>
 __device__ __noinline__ bool djf_dbl(unsigned mask, dpt* p, int k, int gbase) {
     fp_t X = p->X, Y = p->Y, w = p->w, n;
-    fp_t c = dfp6_cofactor_norm<FULL>(mask, Y, k, gbase, &n);
+    fp_t c = dfp6_cofactor_norm(mask, Y, k, gbase, &n);
     fp_t m = fp_add(n, n);
     fp_t w4 = fp_sqr(fp_sqr_nc(w));
-    fp_t xx = dfp6_mul<FULL>(mask, X, X, k, gbase);
+    fp_t xx = dfp6_mul(mask, X, X, k, gbase);
     fp_t num = fp_add(fp_dbl(xx), xx);
     num = fp_add(num, k == 0 ? w4 : 0);
-    fp_t L = dfp6_mul<FULL>(mask, num, c, k, gbase);
+    fp_t L = dfp6_mul(mask, num, c, k, gbase);
     fp_t m2 = fp_sqr_nc(m), m3 = fp_mul_nc(m2, m);
     fp_t A = fp_mul(X, m2);
-    fp_t X3 = fp_sub(fp_sub(dfp6_mul<FULL>(mask, L, L, k, gbase), A), A);
-    fp_t Y3 = fp_sub(dfp6_mul<FULL>(mask, L, fp_sub(A, X3), k, gbase), fp_mul(Y, m3));
+    fp_t X3 = fp_sub(fp_sub(dfp6_mul(mask, L, L, k, gbase), A), A);
+    fp_t Y3 = fp_sub(dfp6_mul(mask, L, fp_sub(A, X3), k, gbase), fp_mul(Y, m3));
     p->X = X3;
     p->Y = Y3;
     p->w = fp_mul(m, w);
@@ -124,7 +113,6 @@ __device__ __noinline__ bool djf_dbl(unsigned mask, dpt* p, int k, int gbase) {
 }
 
 // acc <- acc (+|-) src by mode (jf_add of affine.cuh)
-template <bool FULL = false>
 __device__ __noinline__ bool djf_add(unsigned mask, dpt* acc, const dpt* src, uint8_t mode, int k, int gbase) {
     fp_t X1 = acc->X, Y1 = acc->Y, w1 = acc->w, X2 = src->X, Y2 = src->Y, w2 = src->w;
     if (mode == JOP_SUB || mode == JOP_SETNEG) Y2 = fp_neg(Y2);
@@ -139,13 +127,13 @@ __device__ __noinline__ bool djf_add(unsigned mask, dpt* acc, const dpt* src, ui
     wide_mac(wa, FP_P - Y2, w1c);
     fp_t num = wide_reduce(wa);
     fp_t n;
-    fp_t c = dfp6_cofactor_norm<FULL>(mask, d, k, gbase, &n);
-    fp_t L = dfp6_mul<FULL>(mask, num, c, k, gbase);
+    fp_t c = dfp6_cofactor_norm(mask, d, k, gbase, &n);
+    fp_t L = dfp6_mul(mask, num, c, k, gbase);
     fp_t n2 = fp_sqr_nc(n), n3 = fp_mul_nc(n2, n);
     fp_t A = fp_mul(X1, fp_mul_nc(n2, w2s));
     fp_t B = fp_mul(X2, fp_mul_nc(n2, w1s));
-    fp_t X3 = fp_sub(fp_sub(dfp6_mul<FULL>(mask, L, L, k, gbase), A), B);
-    fp_t Y3 = fp_sub(dfp6_mul<FULL>(mask, L, fp_sub(A, X3), k, gbase), fp_mul(Y1, fp_mul_nc(n3, w2c)));
+    fp_t X3 = fp_sub(fp_sub(dfp6_mul(mask, L, L, k, gbase), A), B);
+    fp_t Y3 = fp_sub(dfp6_mul(mask, L, fp_sub(A, X3), k, gbase), fp_mul(Y1, fp_mul_nc(n3, w2c)));
     fp_t w3 = fp_mul(fp_mul_nc(n, w1), w2);
     bool wanted = mode == JOP_ADD || mode == JOP_SUB;
     bool active = wanted && n != 0;
@@ -175,13 +163,12 @@ __device__ __forceinline__ void djf_add_exact(unsigned mask, dpt* acc, const dpt
 // ---- Rescue-Prime with the state held two elements per lane: lane k has s[k] (lo) and s[k + 6] (hi) ----
 // y = M s + ark: every lane gathers the 12 inputs by shuffles and forms its two rows of the circulant matrix;
 // `mds2` = the MDS row twice (shared memory): M[i][j] = row[(j - i) mod 12] = mds2[j - i + 12]
-template <bool FULL = false>
 __device__ __forceinline__ void drescue_mds_ark(unsigned mask, fp_t& lo, fp_t& hi, int ark_row, int k, int gbase,
                                                 const uint32_t* mds2) {
     uint64_t alo = 0, ahi = 0, blo = 0, bhi = 0;  // rows k (a) and k + 6 (b): low / high input halves, no carries
 #pragma unroll
     for (int j = 0; j < 12; j++) {
-        fp_t v = dshfl<FULL>(mask, j < 6 ? lo : hi, gbase + (j % 6));
+        fp_t v = dshfl(mask, j < 6 ? lo : hi, gbase + (j % 6));
         uint32_t ma = mds2[j - k + 12], mb = mds2[j - k + 6];
         alo += (uint64_t)(uint32_t)v * ma;
         ahi += (v >> 32) * ma;
@@ -193,31 +180,29 @@ __device__ __forceinline__ void drescue_mds_ark(unsigned mask, fp_t& lo, fp_t& h
     mid = (blo >> 32) + bhi;
     hi = fp_add(fp_reduce96((uint32_t)blo, (uint32_t)mid, (uint32_t)(mid >> 32)), SB_ARK(ark_row * 12 + k + 6));
 }
-template <bool FULL = false>
 __device__ __noinline__ void drescue_permutation(unsigned mask, fp_t* lo_hi, int k, int gbase, const uint32_t* mds2) {
     fp_t s[2] = {lo_hi[0], lo_hi[1]};
 #pragma unroll 1
     for (int r = 0; r < RESCUE_ROUNDS; r++) {
         s[0] = rescue_sbox(s[0]);
         s[1] = rescue_sbox(s[1]);
-        drescue_mds_ark<FULL>(mask, s[0], s[1], 2 * r, k, gbase, mds2);
+        drescue_mds_ark(mask, s[0], s[1], 2 * r, k, gbase, mds2);
         rescue_inv_sbox_lanes<2>(s);
-        drescue_mds_ark<FULL>(mask, s[0], s[1], 2 * r + 1, k, gbase, mds2);
+        drescue_mds_ark(mask, s[0], s[1], 2 * r + 1, k, gbase, mds2);
     }
     lo_hi[0] = s[0];
     lo_hi[1] = s[1];
 }
 // hash_message (rescue.cuh) on six lanes; rx, px, py = the lane's coefficients (py: only lane 0's P.y[0] is used);
 // msg/len are the group's message; the digest (4 elements) is returned on every lane
-template <bool FULL = false>
 __device__ void dhash_message(unsigned mask, fp_t rx, fp_t px, fp_t py, const uint8_t* msg, uint64_t len, int k, int gbase,
                               const uint32_t* mds2, fp_t* d) {
     fp_t s[2];
     s[0] = rx;               // s[0..5] = R.x
     s[1] = k < 2 ? px : 0;   // s[6], s[7] = P.x[0..1]; capacity = 0
-    drescue_permutation<FULL>(mask, s, k, gbase, mds2);
+    drescue_permutation(mask, s, k, gbase, mds2);
     // s[0..3] += P.x[2..5], s[4] += P.y[0]
-    fp_t t1 = dshfl<FULL>(mask, px, gbase + (k + 2 < 6 ? k + 2 : 5)), t2 = dshfl<FULL>(mask, py, gbase);
+    fp_t t1 = dshfl(mask, px, gbase + (k + 2 < 6 ? k + 2 : 5)), t2 = dshfl(mask, py, gbase);
     s[0] = fp_add(s[0], k < 4 ? t1 : (k == 4 ? t2 : 0));
     int pos = 5;
     uint64_t nb = len / 7;
@@ -229,7 +214,7 @@ __device__ void dhash_message(unsigned mask, fp_t rx, fp_t px, fp_t py, const ui
         if (pos >= 6) s[1] = fp_add(s[1], v);
         else s[0] = fp_add(s[0], v);
         if (++pos == 8) {
-            drescue_permutation<FULL>(mask, s, k, gbase, mds2);
+            drescue_permutation(mask, s, k, gbase, mds2);
             pos = 0;
         }
     }
@@ -237,17 +222,16 @@ __device__ void dhash_message(unsigned mask, fp_t rx, fp_t px, fp_t py, const ui
         fp_t v = (k == pos % 6) ? 1 : 0;
         if (pos >= 6) s[1] = fp_add(s[1], v);
         else s[0] = fp_add(s[0], v);
-        drescue_permutation<FULL>(mask, s, k, gbase, mds2);
+        drescue_permutation(mask, s, k, gbase, mds2);
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) d[i] = dshfl<FULL>(mask, s[0], gbase + i);
+    for (int i = 0; i < 4; i++) d[i] = dshfl(mask, s[0], gbase + i);
 }
 // challenge scalar (verify.cuh: challenge_scalar)
-template <bool FULL = false>
 __device__ scalar dchallenge_scalar(unsigned mask, fp_t rx, fp_t px, fp_t py, const uint8_t* msg, uint64_t len, int k,
                                     int gbase, const uint32_t* mds2) {
     fp_t d[4];
-    dhash_message<FULL>(mask, rx, px, py, msg, len, k, gbase, mds2, d);
+    dhash_message(mask, rx, px, py, msg, len, k, gbase, mds2, d);
     return digest_to_scalar(d);
 }
 

@@ -382,8 +382,6 @@ __global__ void __launch_bounds__(DIST_THREADS) k_verify_dist(soa_batch in, cons
     }
 }
 
-// K2 for the smallest calls: one thread block per signature (needs soa_batch and the ingest flags defined above)
-#include "one.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K1: hash_message, one message per thread (AoS inputs: 8-byte aligned records)
@@ -784,6 +782,9 @@ static int verify_many_host(schnorr_b200_ctx* ctx, size_t n, const uint8_t* sigs
                             const uint8_t* msgs, const uint64_t* msg_off, uint8_t* verdicts, bool validate_offsets);
 #include "batch.cuh"
 #include "multi.cuh"
+// K2 for the smallest calls: one thread block per signature (uses the six-lane primitives of dist.cuh and the 24-lane
+// Jacobian toolkit of batch.cuh)
+#include "one.cuh"
 
 
 // Signature::verify over an ingested SoA batch: fast path (per-thread or warp-cooperative by call size), then the exact kernel over the handful of
@@ -805,7 +806,10 @@ static int launch_verify(schnorr_b200_ctx* ctx, const soa_batch& soa, const uint
     CUDA_TRY(ctx, cudaMemsetAsync(counters + counter, 0, 4, st));
     if (counter + 1 > ctx->exact_counters_used) ctx->exact_counters_used = counter + 1;
     if (soa.n <= ctx->one_max)
-        k_verify_one<<<(unsigned)soa.n, ONE_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+        if (soa.n <= (size_t)2 * ctx->sm_count)   // every block resident at two per SM: the full register budget
+            k_verify_one<2><<<(unsigned)soa.n, ONE_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
+        else
+            k_verify_one<4><<<(unsigned)soa.n, ONE_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list, counters + counter);
     else if (soa.n <= ctx->dist_max)
         k_verify_dist<<<grid_for(soa.n, DIST_SIGS_PER_BLOCK), DIST_THREADS, 0, st>>>(soa, msgs, msg_off, ctx->gtab, verdicts, list,
                                                                                    counters + counter);
