@@ -99,6 +99,12 @@ int schnorr_b200_set_one_threshold(schnorr_b200_ctx *ctx, size_t max_signatures)
 /* Batches of at most `max_signatures` compute their challenges with one signature per six lanes ahead of the (then
  * hash-free) prepare kernel; larger ones hash one signature per thread.  Default 2^18 (measured crossover). */
 int schnorr_b200_set_batch_dist_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
+/* Batches (per device) of at most `max_signatures` signatures run one thread block per signature: block i evaluates its
+ * own term s_i R_i - s_i h_i P_i of the batch equation (src/batch.rs:102-123) with the two doubling chains, the challenge
+ * hash and the bucket accumulations side by side on its warps, and one more block adds the terms -- the latency form for
+ * the reference's Criterion cases of 4 ... 128 signatures (benches/schnorr.rs:67-96).  Larger batches take the Pippenger
+ * pipeline.  0 disables it.  Default 256. */
+int schnorr_b200_set_batch_small_threshold(schnorr_b200_ctx *ctx, size_t max_signatures);
 /* Test hook: force the Pippenger window width (4..16, 0 = planner's choice) and the segment length of the bucket
  * accumulation (>= 8, 0 = automatic) of the batch path, to exercise the skewed-bucket code paths. */
 int schnorr_b200_set_msm_geometry(schnorr_b200_ctx *ctx, int window_bits, unsigned segment_len);

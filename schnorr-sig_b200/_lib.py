@@ -26,6 +26,7 @@ _SIGNATURES = {
     "schnorr_b200_last_exact_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "schnorr_b200_set_dist_threshold": (C.c_int, [C.c_void_p, _sz]),
     "schnorr_b200_set_one_threshold": (C.c_int, [C.c_void_p, _sz]),
+    "schnorr_b200_set_batch_small_threshold": (C.c_int, [C.c_void_p, _sz]),
     "schnorr_b200_set_batch_dist_threshold": (C.c_int, [C.c_void_p, _sz]),
     "schnorr_b200_set_msm_geometry": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
     "schnorr_b200_last_batch_plan": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint)]),

@@ -792,6 +792,253 @@ __global__ void __launch_bounds__(VERIFY_THREADS, VERIFY_MIN_BLOCKS) k_batch_ite
     out[i] = same ? VERDICT_OK : VERDICT_INVALID_SIGNATURE;
 }
 
+// ---- small batches: one thread block per signature -------------------------------------------------------------------
+// A batch of a few signatures (the reference's Criterion cases are 4 ... 128, benches/schnorr.rs:67-96) is pure latency in
+// the Pippenger pipeline above: sixteen launches, a counting sort for a hundred points, a Horner tail of 255 serial
+// doublings.  Here block i evaluates its own term of the batch equation (src/batch.rs:102-123),
+//     T_i = s_i R_i + (s_i h_i) (-P_i),
+// as k_verify_one does for a single verification (one.cuh): the two doubling chains of R_i and -P_i run side by side on
+// two warps (24-lane Jacobian toolkit above, only the 64 window points of each chain are kept), a third warp hashes the
+// challenge and forms the scalars, then the sixteen bucket accumulations (signed 4-bit windows: eight buckets per point)
+// run four per warp and the two aggregations on two warps.  k_batch_small_reduce adds the T_i (eight per warp, then a tree)
+// and writes the same 192-byte partial as k_msm_horner.  All arithmetic is exact (jac_add_dist_exact).
+static constexpr int SMALL_THREADS = 128;
+static constexpr int SMALL_WINDOWS = 64;   // signed 4-bit windows of a scalar < q < 2^255
+
+// acc += (x2, y2, z2) on the 24 lanes, exact: the distributed formula, or -- identity operand / equal x -- the complete
+// per-thread addition, every lane redundantly
+__device__ __forceinline__ void jac_add_dist_exact(fp_t& x, fp_t& y, fp_t& z, fp_t x2, fp_t y2, fp_t z2, int g, int k) {
+    if (__ballot_sync(HORNER_MASK, z2 == 0) == HORNER_MASK) return;   // + identity
+    if (__ballot_sync(HORNER_MASK, z == 0) == HORNER_MASK) {          // identity + src
+        x = x2;
+        y = y2;
+        z = z2;
+        return;
+    }
+    if (!jac_add_dist(x, y, z, x2, y2, z2, g, k)) {
+        jac_pt a, b;
+        a.X = gather_fp6(x);
+        a.Y = gather_fp6(y);
+        a.Z = gather_fp6(z);
+        b.X = gather_fp6(x2);
+        b.Y = gather_fp6(y2);
+        b.Z = gather_fp6(z2);
+        jac_add_mem(&a, &b, false);
+        x = a.X.c[k];
+        y = a.Y.c[k];
+        z = a.Z.c[k];
+    }
+}
+
+struct small_shared {
+    fp_t cx[2][SMALL_WINDOWS][6], cy[2][SMALL_WINDOWS][6], cz[2][SMALL_WINDOWS][6];  // window points 16^w R (0) and 16^w (-P) (1)
+    fp_t bx[16][6], by[16][6], bz[16][6];                                             // bucket sums: 0..7 of R, 8..15 of -P
+    fp_t ax[6], ay[6], az[6];                                                         // aggregated s_p (-P)
+    fp_t rxy[12];                                                                     // decompressed R
+    uint32_t mds2[24];
+    int8_t hd[2][SMALL_WINDOWS];
+    uint8_t lst[16][SMALL_WINDOWS], neg[16][SMALL_WINDOWS];
+    int cnt[16];
+    int ok, r_inf;
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_batch_small(soa_batch in, const uint8_t* __restrict__ msgs,
+                                                               const uint64_t* __restrict__ msg_off,
+                                                               const uint8_t* __restrict__ rand32, uint64_t* __restrict__ terms,
+                                                               uint32_t* __restrict__ lin, int* __restrict__ bad) {
+    __shared__ small_shared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool in24 = lane < 24;
+    const int g = in24 ? lane / 6 : 0, k = lane % 6;
+    const size_t i = blockIdx.x, n = in.n;
+    const uint8_t fl = in.flags[i];
+    const bool pk_inf = fl & FL_PK_INF;
+    if (tid < 24) S.mds2[tid] = c_mds_row[tid % 12];
+    if (tid < 16) S.cnt[tid] = 0;
+    const uint64_t* pl = reinterpret_cast<const uint64_t*>(in.planes);
+    fp_t sx = pl[((size_t)(0 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    fp_t px = pl[((size_t)(5 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    fp_t py = pl[((size_t)(8 + (k >> 1)) * n + i) * 2 + (k & 1)];
+    if (tid == 0) {   // R = from_compressed(sig.x) incl. its flag byte: the reference unwraps it (src/batch.rs:104)
+        bool ok = !(fl & (FL_MALFORMED | FL_X_BAD));
+        fp6 rx = fp6_zero(), ry = fp6_zero();
+        bool r_inf = true;
+        if (ok) ok = decompress_point(load_fp6_planes(in.planes, 0, n, i), in.sig_flag[i], rx, ry, r_inf);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            S.rxy[c] = rx.c[c];
+            S.rxy[6 + c] = ry.c[c];
+        }
+        S.ok = ok;
+        S.r_inf = r_inf;
+        if (!ok) atomicOr(bad, 1);
+    }
+    __syncthreads();
+    const bool ok = S.ok != 0, r_inf = S.r_inf != 0;
+
+    // ---- phase A: the two doubling chains | challenge and scalars ----------------------------------------------------
+    if (warp < 2) {
+        const bool skip = warp == 0 ? (!ok || r_inf) : (!ok || pk_inf);   // identity contributes nothing
+        if (in24 && !skip) {
+            fp_t x = warp == 0 ? S.rxy[k] : px;
+            fp_t y = warp == 0 ? S.rxy[6 + k] : fp_neg(py);               // -P, src/batch.rs:106
+            fp_t z = k == 0 ? 1 : 0;
+#pragma unroll 1
+            for (int w = 0; w < SMALL_WINDOWS; w++) {
+                if (g == 0) {
+                    S.cx[warp][w][k] = x;
+                    S.cy[warp][w][k] = y;
+                    S.cz[warp][w][k] = z;
+                }
+                if (w < SMALL_WINDOWS - 1) {
+                    jac_dbl_dist(x, y, z, g, k);
+                    jac_dbl_dist(x, y, z, g, k);
+                    jac_dbl_dist(x, y, z, g, k);
+                    jac_dbl_dist(x, y, z, g, k);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane < 6) {
+            uint64_t off = msg_off[i];
+            scalar h = dchallenge_scalar(0x3fu, sx, pk_inf ? 0 : px, pk_inf ? 0 : py, msgs + off, msg_off[i + 1] - off, k, 0, S.mds2);
+            if (k == 0) {
+                scalar e = load_scalar_planes(in.planes, 3, n, i);
+                scalar s = sc_from_u256(sc_load_le(rand32 + 32 * i));
+                scalar s_r = sc_zero(), s_p = sc_zero(), l = sc_zero();
+                if (ok) {
+                    l = sc_mul(s, e);                         // src/batch.rs:92-97
+                    s_r = r_inf ? sc_zero() : s;
+                    s_p = pk_inf ? sc_zero() : sc_mul(h, s);  // src/batch.rs:109-111
+                }
+                recode_signed_w4(s_r, S.hd[0]);
+                recode_signed_w4(s_p, S.hd[1]);
+#pragma unroll
+                for (int c = 0; c < 8; c++) lin[i * 8 + c] = l.l[c];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: sixteen bucket accumulations, four per warp --------------------------------------------------------
+    if (in24) {
+#pragma unroll 1
+        for (int q4 = 0; q4 < 4; q4++) {
+            const int slot = warp * 4 + q4, which = slot >> 3, mag = (slot & 7) + 1;
+            if (lane == 0) {
+                int c = 0;
+#pragma unroll 1
+                for (int w = 0; w < SMALL_WINDOWS; w++) {
+                    int d = S.hd[which][w];
+                    if (d != 0 && (d < 0 ? -d : d) == mag) {
+                        S.lst[slot][c] = (uint8_t)w;
+                        S.neg[slot][c] = d < 0;
+                        c++;
+                    }
+                }
+                S.cnt[slot] = c;
+            }
+            __syncwarp(HORNER_MASK);
+            const int cnt = S.cnt[slot];
+            fp_t x = 1, y = 1, z = 0;
+#pragma unroll 1
+            for (int t = 0; t < cnt; t++) {
+                int w = S.lst[slot][t];
+                fp_t x2 = S.cx[which][w][k], y2 = S.cy[which][w][k], z2 = S.cz[which][w][k];
+                if (S.neg[slot][t]) y2 = fp_neg(y2);
+                if (t == 0) {
+                    x = x2;
+                    y = y2;
+                    z = z2;
+                } else {
+                    jac_add_dist_exact(x, y, z, x2, y2, z2, g, k);
+                }
+            }
+            if (g == 0) {
+                S.bx[slot][k] = x;
+                S.by[slot][k] = y;
+                S.bz[slot][k] = z;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: sum_m m B_m for both points (running sums), then T_i ------------------------------------------------
+    fp_t ox = 1, oy = 1, oz = 0;
+    if (warp < 2 && in24) {
+        const int base = 8 * warp;
+        fp_t rx = S.bx[base + 7][k], ry = S.by[base + 7][k], rz = S.bz[base + 7][k];
+        ox = rx;
+        oy = ry;
+        oz = rz;
+#pragma unroll 1
+        for (int b = 6; b >= 0; b--) {
+            jac_add_dist_exact(rx, ry, rz, S.bx[base + b][k], S.by[base + b][k], S.bz[base + b][k], g, k);
+            jac_add_dist_exact(ox, oy, oz, rx, ry, rz, g, k);
+        }
+        if (warp == 1 && g == 0) {
+            S.ax[k] = ox;
+            S.ay[k] = oy;
+            S.az[k] = oz;
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && in24) {
+        jac_add_dist_exact(ox, oy, oz, S.ax[k], S.ay[k], S.az[k], g, k);
+        if (g == 0) {
+            uint64_t* o = terms + i * 18;
+            o[k] = ox;
+            o[6 + k] = oy;
+            o[12 + k] = oz;
+        }
+    }
+}
+
+// partial192 = sum of the n terms (Jacobian) || partial scalar sum || bad flag, as k_msm_horner writes it
+static constexpr int SMALL_REDUCE_THREADS = 512;
+__global__ void __launch_bounds__(SMALL_REDUCE_THREADS) k_batch_small_reduce(size_t n, const uint64_t* __restrict__ terms,
+                                                                              const uint32_t* __restrict__ lin_total,
+                                                                              const int* __restrict__ bad,
+                                                                              uint64_t* __restrict__ partial) {
+    __shared__ fp_t sx[SMALL_REDUCE_THREADS / 32][6], sy[SMALL_REDUCE_THREADS / 32][6], sz[SMALL_REDUCE_THREADS / 32][6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = SMALL_REDUCE_THREADS / 32;
+    const bool in24 = lane < 24;
+    const int g = in24 ? lane / 6 : 0, k = lane % 6;
+    fp_t x = 1, y = 1, z = 0;
+    if (in24) {
+#pragma unroll 1
+        for (size_t i = warp; i < n; i += nw) {
+            const uint64_t* t = terms + i * 18;
+            jac_add_dist_exact(x, y, z, t[k], t[6 + k], t[12 + k], g, k);
+        }
+        if (g == 0) {
+            sx[warp][k] = x;
+            sy[warp][k] = y;
+            sz[warp][k] = z;
+        }
+    }
+#pragma unroll 1
+    for (int d = nw / 2; d > 0; d >>= 1) {
+        __syncthreads();
+        if (warp < d && in24) {
+            jac_add_dist_exact(x, y, z, sx[warp + d][k], sy[warp + d][k], sz[warp + d][k], g, k);
+            if (g == 0) {
+                sx[warp][k] = x;
+                sy[warp][k] = y;
+                sz[warp][k] = z;
+            }
+        }
+    }
+    if (warp == 0 && in24 && g == 0) {
+        partial[k] = x;
+        partial[6 + k] = y;
+        partial[12 + k] = z;
+        if (k < 4) partial[18 + k] = ((uint64_t)lin_total[2 * k + 1] << 32) | lin_total[2 * k];
+        if (k == 4) partial[22] = (uint64_t)(*bad != 0);
+        if (k == 5) partial[23] = 0;
+    }
+}
+
 // ---- host orchestration ----------------------------------------------------------------------
 // rhs_pre (optional, device, 13 x u64): single-device batches get (sum s_i e_i) G computed on the second stream beside the
 // MSM; the caller's finish kernel must wait on ctx->ev_aux
@@ -800,6 +1047,39 @@ static int batch_partial_impl(schnorr_b200_ctx* ctx, size_t n, const uint8_t* si
                               const uint8_t* rand32, uint8_t* partial192, uint64_t* rhs_pre = nullptr) {
     soa_batch soa;
     if (int rc = alloc_soa(ctx, n, &soa)) return rc;
+    if (n <= ctx->batch_small_max) {   // one thread block per signature (latency), see k_batch_small
+        void *d_terms, *d_lin, *d_small;
+        if (int rc = ensure_scratch(ctx, SL_D, n * 18 * 8, &d_terms)) return rc;
+        if (int rc = ensure_scratch(ctx, SL_F, n * 32 + 512 * 32, &d_lin)) return rc;
+        if (int rc = ensure_scratch(ctx, SL_L, 64, &d_small)) return rc;
+        uint32_t* lin = (uint32_t*)d_lin;
+        uint32_t* lin_part = lin + n * 8;
+        uint32_t* lin_total = lin_part + 256 * 8;
+        int* bad = (int*)d_small;
+        cudaStream_t st = ctx->stream;
+        CUDA_TRY(ctx, cudaMemsetAsync(d_small, 0, 64, st));
+        k_ingest<<<grid_for(n, INGEST_THREADS), INGEST_THREADS, 0, st>>>(n, sigs81, pk96, pk_inf, soa);
+        cudaEventRecord(ctx->ev_k0, st);
+        k_batch_small<<<(unsigned)n, SMALL_THREADS, 0, st>>>(soa, msgs, msg_off, rand32, (uint64_t*)d_terms, lin, bad);
+        cudaEventRecord(ctx->ev_k1, st);
+        int sum_blocks = (int)((n + 255) / 256);
+        k_scalar_sum<<<sum_blocks, 256, 0, st>>>(lin, n, lin_part);
+        k_scalar_sum<<<1, 256, 0, st>>>(lin_part, (size_t)sum_blocks, lin_total);
+        if (rhs_pre) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_chunk[1], st));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_chunk[1], 0));
+            k_lin_times_g<<<1, 32, 0, ctx->aux_stream>>>(lin_total, ctx->gtab, rhs_pre);
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_aux, ctx->aux_stream));
+            ctx->launches += 1;
+        }
+        k_batch_small_reduce<<<1, SMALL_REDUCE_THREADS, 0, st>>>(n, (uint64_t*)d_terms, lin_total, bad, (uint64_t*)partial192);
+        ctx->last_msm_c = 4;
+        ctx->last_msm_K = SMALL_WINDOWS;
+        ctx->last_msm_T = 0;
+        ctx->launches += 5;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return SCHNORR_B200_OK;
+    }
     size_t npts = 2 * n;
     if (npts >= 0x7fffffffu) {
         ctx->err = "batch too large for 31-bit point indices";

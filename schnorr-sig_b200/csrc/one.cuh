@@ -39,24 +39,6 @@ struct one_shared {
     int e_empty, torsion_free;
 };
 
-// acc += (x2, y2, z2) on the 24 lanes, exact: the distributed formula, or -- identity operand / equal x -- the complete
-// per-thread addition, every lane redundantly
-__device__ __forceinline__ void one_add(fp_t& x, fp_t& y, fp_t& z, fp_t x2, fp_t y2, fp_t z2, int g, int k) {
-    if (!jac_add_dist(x, y, z, x2, y2, z2, g, k)) {
-        jac_pt a, b;
-        a.X = gather_fp6(x);
-        a.Y = gather_fp6(y);
-        a.Z = gather_fp6(z);
-        b.X = gather_fp6(x2);
-        b.Y = gather_fp6(y2);
-        b.Z = gather_fp6(z2);
-        jac_add_mem(&a, &b, false);
-        x = a.X.c[k];
-        y = a.Y.c[k];
-        z = a.Z.c[k];
-    }
-}
-
 // MINB = resident blocks per SM the register allocation must allow: 2 (248 registers, no spills) while every block of the
 // call is resident anyway (n <= 2 x SMs), 4 (128 registers; the rarely taken exact routines spill) beyond
 template <int MINB>
@@ -184,7 +166,7 @@ __global__ void __launch_bounds__(ONE_THREADS, MINB) k_verify_one(soa_batch in, 
                     y = y2;
                     z = z2;
                 } else {
-                    one_add(x, y, z, x2, y2, z2, g, k);
+                    jac_add_dist_exact(x, y, z, x2, y2, z2, g, k);
                 }
             }
             if (g == 0) {
@@ -202,11 +184,11 @@ __global__ void __launch_bounds__(ONE_THREADS, MINB) k_verify_one(soa_batch in, 
         fp_t ox = rx, oy = ry, oz = rz;
 #pragma unroll 1
         for (int b = 6; b >= 0; b--) {
-            one_add(rx, ry, rz, S.bx[b][k], S.by[b][k], S.bz[b][k], g, k);
-            if (b >= 1) one_add(ox, oy, oz, rx, ry, rz, g, k);
+            jac_add_dist_exact(rx, ry, rz, S.bx[b][k], S.by[b][k], S.bz[b][k], g, k);
+            if (b >= 1) jac_add_dist_exact(ox, oy, oz, rx, ry, rz, g, k);
         }
         jac_dbl_dist(ox, oy, oz, g, k);
-        one_add(ox, oy, oz, rx, ry, rz, g, k);
+        jac_add_dist_exact(ox, oy, oz, rx, ry, rz, g, k);
         bool ident = __ballot_sync(HORNER_MASK, oz == 0) == HORNER_MASK;
         if (lane == 0) S.torsion_free = ident;
     }
@@ -217,11 +199,11 @@ __global__ void __launch_bounds__(ONE_THREADS, MINB) k_verify_one(soa_batch in, 
         fp_t ox = rx, oy = ry, oz = rz;
 #pragma unroll 1
         for (int b = 6; b >= 0; b--) {
-            one_add(rx, ry, rz, S.bx[8 + b][k], S.by[8 + b][k], S.bz[8 + b][k], g, k);
-            one_add(ox, oy, oz, rx, ry, rz, g, k);
+            jac_add_dist_exact(rx, ry, rz, S.bx[8 + b][k], S.by[8 + b][k], S.bz[8 + b][k], g, k);
+            jac_add_dist_exact(ox, oy, oz, rx, ry, rz, g, k);
         }
         fp_t ez = (S.e_empty == 0 && k == 0) ? S.ew : 0;
-        one_add(ox, oy, oz, S.ex[k], S.ey[k], ez, g, k);
+        jac_add_dist_exact(ox, oy, oz, S.ex[k], S.ey[k], ez, g, k);
         jac_pt R;
         R.X = gather_fp6(ox);
         R.Y = gather_fp6(oy);

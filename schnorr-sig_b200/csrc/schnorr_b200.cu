@@ -55,6 +55,7 @@ struct schnorr_b200_ctx {
     size_t dist_max = 10240;                        // calls up to this many signatures use the six-lanes-per-signature kernel
     size_t one_max = 512;                           // ... and up to this many the block-per-signature kernel (one.cuh)
     size_t batch_dist_max = (size_t)1 << 18;        // batches up to this size hash their challenges on six lanes per signature
+    size_t batch_small_max = 256;                   // batches up to this size run one thread block per signature (k_batch_small)
     int exact_counters_used = 0;                    // work-list counters written by the last verify call
     static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
@@ -1001,6 +1002,12 @@ int schnorr_b200_set_one_threshold(schnorr_b200_ctx* ctx, size_t max_signatures)
     if (!ctx) return SCHNORR_B200_EARG;
     for (schnorr_b200_ctx* sh : ctx->shards) sh->one_max = max_signatures;
     ctx->one_max = max_signatures;
+    return SCHNORR_B200_OK;
+}
+int schnorr_b200_set_batch_small_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {
+    if (!ctx) return SCHNORR_B200_EARG;
+    for (schnorr_b200_ctx* sh : ctx->shards) sh->batch_small_max = max_signatures;
+    ctx->batch_small_max = max_signatures;
     return SCHNORR_B200_OK;
 }
 int schnorr_b200_set_batch_dist_threshold(schnorr_b200_ctx* ctx, size_t max_signatures) {

@@ -118,6 +118,10 @@ class Engine:
         """Calls up to this many signatures use the block-per-signature kernel (0 = never)."""
         self._check(self._L.schnorr_b200_set_one_threshold(self._h, int(max_signatures)), "set_one_threshold")
 
+    def set_batch_small_threshold(self, max_signatures: int):
+        """Batches up to this size run one thread block per signature (0 = never: always the Pippenger pipeline)."""
+        self._check(self._L.schnorr_b200_set_batch_small_threshold(self._h, int(max_signatures)), "set_batch_small_threshold")
+
     def set_batch_dist_threshold(self, max_signatures: int):
         """Batches up to this size hash their challenges on six lanes per signature (0 = never)."""
         self._check(self._L.schnorr_b200_set_batch_dist_threshold(self._h, int(max_signatures)), "set_batch_dist_threshold")

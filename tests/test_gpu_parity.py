@@ -277,6 +277,9 @@ def test_compress_decompress_round_trip(eng):
 
 
 # ---- K3/K4: batch verification ----------------------------------------------------------------
+BATCH_SMALL_DEFAULT = 256   # schnorr_b200_set_batch_small_threshold default (include/schnorr_b200.h)
+
+
 @pytest.mark.parametrize("n", [1, 3, 5, 64, 700])
 def test_verify_batch_points_bit_exact(eng, n):
     lens = [24, 24, 48] if n == 3 else [int(x) for x in np.random.default_rng(n).integers(0, 90, n)]
@@ -289,11 +292,18 @@ def test_verify_batch_points_bit_exact(eng, n):
     cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"], cref.default_threads())
     assert v == cv == 0
     assert np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
-    eng.set_dist_threshold(0)                         # challenges hashed inside k_batch_prepare (the large-batch form)
+    # the other batch form: Pippenger pipeline for the small sizes (default: one thread block per signature up to 256),
+    # block per signature for the large one
+    eng.set_batch_small_threshold(0 if n <= BATCH_SMALL_DEFAULT else 2**62)
     try:
+        v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"])
+        assert v == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+        eng.set_batch_small_threshold(0)
+        eng.set_dist_threshold(0)                     # challenges hashed inside k_batch_prepare (the large-batch form)
         v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], w["rand"])
     finally:
         eng.set_dist_threshold(10240)
+        eng.set_batch_small_threshold(BATCH_SMALL_DEFAULT)
     assert v == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
     if n >= 5:
         pk2 = w["pk"].copy(); pk2[[1, 2]] = pk2[[2, 1]]
@@ -301,9 +311,14 @@ def test_verify_batch_points_bit_exact(eng, n):
         cv, cl, cr = cref.verify_batch(w["sigs"], pk2, w["inf"], w["blob"], w["off"], w["rand"], cref.default_threads())
         assert v == cv == 2 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
     s2 = w["sigs"].copy(); s2[0, 48] ^= 0x40          # y-sign flag matters here (src/batch.rs:104)
-    assert eng.verify_batch(s2, w["pk"], w["inf"], w["blob"], w["off"], w["rand"])[0] == 2
     s3 = w["sigs"].copy(); s3[0, :8] = 0xFF           # panic in the reference
-    assert eng.verify_batch(s3, w["pk"], w["inf"], w["blob"], w["off"], w["rand"])[0] == 3
+    for thr in (BATCH_SMALL_DEFAULT, 0, 2**62):       # both batch forms
+        eng.set_batch_small_threshold(thr)
+        try:
+            assert eng.verify_batch(s2, w["pk"], w["inf"], w["blob"], w["off"], w["rand"])[0] == 2
+            assert eng.verify_batch(s3, w["pk"], w["inf"], w["blob"], w["off"], w["rand"])[0] == 3
+        finally:
+            eng.set_batch_small_threshold(BATCH_SMALL_DEFAULT)
     assert cref.verify_batch(s3, w["pk"], w["inf"], w["blob"], w["off"], w["rand"], 2)[0] == 3
 
 
@@ -314,9 +329,14 @@ def test_verify_batch_extreme_randomisers_and_empty(eng):
     rand[1] = np.frombuffer((o.Q - 1).to_bytes(32, "little"), np.uint8)   # s = q-1
     rand[2] = 0xFF                                                        # non-canonical: reduced mod q
     rand[3] = 0; rand[3, 0] = 1                                           # s = 1
-    v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], rand)
     cv, cl, cr = cref.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], rand, 2)
-    assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+    for thr in (BATCH_SMALL_DEFAULT, 0):              # block per signature, Pippenger pipeline
+        eng.set_batch_small_threshold(thr)
+        try:
+            v, lhs, rhs = eng.verify_batch(w["sigs"], w["pk"], w["inf"], w["blob"], w["off"], rand)
+        finally:
+            eng.set_batch_small_threshold(BATCH_SMALL_DEFAULT)
+        assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
     v, lhs, rhs = eng.verify_batch(np.zeros((0, 81), np.uint8), np.zeros((0, 96), np.uint8), None,
                                    np.zeros(0, np.uint8), np.zeros(1, np.uint64), np.zeros((0, 32), np.uint8))
     assert v == 0 and lhs[96] == 1 and rhs[96] == 1                      # identity == identity

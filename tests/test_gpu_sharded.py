@@ -109,9 +109,14 @@ def test_batch_with_skewed_randomisers_exercises_bucket_splitting():
     blob = np.tile(w["blob"][:8], 64)
     off = np.arange(65, dtype=np.uint64) * np.uint64(8)
     rand = np.repeat(w["rand"][:1], 64, axis=0)
-    v, lhs, rhs = eng.verify_batch(w2["sigs"], w2["pk"], np.zeros(64, np.uint8), blob, off, rand)
     cv, cl, cr = cref.verify_batch(w2["sigs"], w2["pk"], np.zeros(64, np.uint8), blob, off, rand, 4)
-    assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
+    for thr in (0, 256):      # Pippenger pipeline (P + P inside a bucket), block per signature (P + P in the final sum)
+        eng.set_batch_small_threshold(thr)
+        try:
+            v, lhs, rhs = eng.verify_batch(w2["sigs"], w2["pk"], np.zeros(64, np.uint8), blob, off, rand)
+        finally:
+            eng.set_batch_small_threshold(256)
+        assert v == cv == 0 and np.array_equal(lhs, cl) and np.array_equal(rhs, cr)
 
 
 def test_batch_with_narrow_top_window_uses_the_block_fixup():
