@@ -55,6 +55,8 @@ extern "C" {
     pub fn schnorr_b200_derive_public_children(ctx: *mut schnorr_b200_ctx, n: usize, parent_xpk81: *const u8,
         indices: *const u32, children_xpk81: *mut u8, ok: *mut u8) -> c_int;
     pub fn schnorr_b200_set_dist_threshold(ctx: *mut schnorr_b200_ctx, max_signatures: usize) -> c_int;
+    pub fn schnorr_b200_set_one_threshold(ctx: *mut schnorr_b200_ctx, max_signatures: usize) -> c_int;
+    pub fn schnorr_b200_set_batch_small_threshold(ctx: *mut schnorr_b200_ctx, max_signatures: usize) -> c_int;
     pub fn schnorr_b200_set_msm_geometry(ctx: *mut schnorr_b200_ctx, window_bits: c_int, segment_len: c_uint) -> c_int;
 }
 
